@@ -1,0 +1,309 @@
+// fa_api.cu — the C ABI declared in include/fa_b200.h: argument validation, TMA tensor-map
+// construction, kernel dispatch.  Host-side counterpart of the reference launchers
+// (flash_attention_v1/CUDA/flash_attention_v1.h:251-293, flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:312-354,
+// flash_attention_v2/CUDA/flash_attention_v2.h:438-509) without their per-call device queries, allocations and syncs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/fa_b200.h"
+#include "fa_combine_sm100.cuh"
+#include "fa_fwd_sm100.cuh"
+#include "fa_tiled_d_sm100.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define FA_CUDA_TRY(expr)                                                                           \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(FA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+int elem_size(int dtype) { return dtype == FA_DTYPE_F32 ? 4 : 2; }
+
+// [BH][L][D] row-major tensor, box = one 128-byte-wide, `box_rows`-row block of one head, 128B swizzle.
+// Rows past L are zero-filled on load and clipped on store, so tiles never leak into the next head.
+int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows) {
+  EncodeFn enc = get_encode_fn();
+  if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = elem_size(dtype);
+  CUtensorMapDataType dt = dtype == FA_DTYPE_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[3] = {cuuint64_t(D), cuuint64_t(L), cuuint64_t(BH)};
+  cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(L) * D * es};
+  cuuint32_t box[3] = {cuuint32_t(128 / es), cuuint32_t(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return FA_OK;
+}
+
+int check_common(const void* Q, const void* K, const void* V, const void* O, int B, int H, int L, int d, int dtype) {
+  if (B <= 0 || H <= 0 || L <= 0 || d <= 0) return fail(FA_ERR_SHAPE, "B, H, L, d must be positive");
+  if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F16)
+    return fail(FA_ERR_DTYPE, "dtype must be FA_DTYPE_F32, FA_DTYPE_BF16 or FA_DTYPE_F16");
+  const void* ptrs[4] = {Q, K, V, O};
+  for (const void* p : ptrs)
+    if (p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) != 0)
+      return fail(FA_ERR_ALIGN, "Q, K, V, O must be non-null and 16-byte aligned");
+  return FA_OK;
+}
+
+template <int D, int DT, bool SPLIT>
+int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int kv_per_split, int n_splits,
+               float* o_accum, float* lse_accum, cudaStream_t stream) {
+  using T = fa::FwdTraits<D, DT>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if (SPLIT) {
+    tmO = tmQ;  // unused by the split epilogue
+  } else if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) {
+    return rc;
+  }
+  fa::FwdParams p;
+  p.L = L;
+  p.BH = BH;
+  p.kv_per_split = SPLIT ? kv_per_split : L;
+  p.n_splits = SPLIT ? n_splits : 1;
+  p.scale = 1.0f / std::sqrt(float(D));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.o_accum = o_accum;
+  p.lse_accum = lse_accum;
+  auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  dim3 grid((L + 255) / 256, BH, SPLIT ? n_splits : 1);
+  kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+template <bool SPLIT>
+int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
+                 int kv_per_split, int n_splits, float* o_accum, float* lse_accum, cudaStream_t s) {
+#define FA_CASE(DD, DTT)                                                                                         \
+  if (d == DD && dtype == DTT)                                                                                   \
+    return launch_fwd<DD, DTT, SPLIT>(Q, K, V, O, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s);
+  FA_CASE(128, fa::DT_BF16)
+  FA_CASE(64, fa::DT_BF16)
+  FA_CASE(128, fa::DT_F16)
+  FA_CASE(64, fa::DT_F16)
+  FA_CASE(32, fa::DT_F32)
+  FA_CASE(64, fa::DT_F32)
+#undef FA_CASE
+  return fail(FA_ERR_UNSUPPORTED_D,
+              "fused-tile kernel serves d in {64,128} for bf16/fp16 and d in {32,64} for fp32; got d=" +
+                  std::to_string(d) + " dtype=" + std::to_string(dtype));
+}
+
+template <int D, int DT>
+int launch_combine(const float* o_accum, const float* lse_accum, void* O, long long rows, int n_splits,
+                   cudaStream_t s) {
+  constexpr int G = (D / 4 < 32) ? D / 4 : 32;
+  constexpr int RPB = fa::kCombineThreads / G;
+  const long long blocks = (rows + RPB - 1) / RPB;
+  fa::fa_combine_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+// cached device staging for the host-buffer entry point
+struct HostStaging {
+  void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t bytes = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::mutex mu;
+} g_stage;
+
+}  // namespace
+
+extern "C" {
+
+const char* fa_last_error(void) { return g_err.c_str(); }
+
+int fa_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+
+int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int dtype,
+                  void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (d > 128) return fa_v1_tiled_d_forward(Q, K, V, O, B, H, L, d, d >= 64 ? 64 : d, d >= 64 ? 64 : d, dtype, stream);
+  return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
+                          int d_tile_qk, int d_tile_v, int dtype, void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  // Same argument contract as the reference launcher (flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:323-328).
+  if (d_tile_qk <= 0 || d_tile_v <= 0 || d % d_tile_qk != 0 || d % d_tile_v != 0)
+    return fail(FA_ERR_SHAPE, "d_tile_qk and d_tile_v must be positive divisors of d");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d <= 128) return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
+  return fa::tiled_d_dispatch(Q, K, V, O, B * H, L, d, dtype, s, &g_err);
+}
+
+int fa_v2_num_splits(int L, int kv_per_split) {
+  if (L <= 0 || kv_per_split <= 0) return 0;
+  return (L + kv_per_split - 1) / kv_per_split;
+}
+
+size_t fa_v2_workspace_bytes(int B, int H, int L, int d, int kv_per_split) {
+  const int ns = fa_v2_num_splits(L, kv_per_split);
+  if (ns <= 0 || B <= 0 || H <= 0 || d <= 0) return 0;
+  const size_t rows = size_t(B) * H * L;
+  const size_t o_bytes = ((size_t(ns) * rows * d * sizeof(float)) + 255) & ~size_t(255);
+  const size_t lse_bytes = ((size_t(ns) * rows * sizeof(float)) + 255) & ~size_t(255);
+  return o_bytes + lse_bytes;
+}
+
+int fa_v2_splitkv_forward(const void* Q, const void* K, const void* V, float* Oaccum, float* LSEaccum, int B, int H,
+                          int L, int d, int kv_per_split, int dtype, void* stream) {
+  int rc = check_common(Q, K, V, Oaccum, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (kv_per_split <= 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
+  if (LSEaccum == nullptr) return fail(FA_ERR_ALIGN, "LSEaccum must be non-null");
+  const int ns = fa_v2_num_splits(L, kv_per_split);
+  return dispatch_fwd<true>(Q, K, V, nullptr, B * H, L, d, dtype, kv_per_split, ns, Oaccum, LSEaccum,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int fa_v2_combine(const float* Oaccum, const float* LSEaccum, void* O, int B, int H, int L, int d, int n_splits,
+                  int dtype, void* stream) {
+  if (B <= 0 || H <= 0 || L <= 0 || d <= 0 || n_splits <= 0) return fail(FA_ERR_SHAPE, "B, H, L, d, n_splits must be positive");
+  if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F16) return fail(FA_ERR_DTYPE, "unknown dtype");
+  if (!Oaccum || !LSEaccum || !O || (reinterpret_cast<uintptr_t>(Oaccum) & 15) || (reinterpret_cast<uintptr_t>(O) & 15))
+    return fail(FA_ERR_ALIGN, "Oaccum, LSEaccum, O must be non-null; Oaccum and O 16-byte aligned");
+  const long long rows = (long long)B * H * L;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define FA_CASE(DD)                                                                                        \
+  if (d == DD) {                                                                                           \
+    if (dtype == FA_DTYPE_F32) return launch_combine<DD, fa::DT_F32>(Oaccum, LSEaccum, O, rows, n_splits, s);   \
+    if (dtype == FA_DTYPE_BF16) return launch_combine<DD, fa::DT_BF16>(Oaccum, LSEaccum, O, rows, n_splits, s); \
+    return launch_combine<DD, fa::DT_F16>(Oaccum, LSEaccum, O, rows, n_splits, s);                          \
+  }
+  FA_CASE(32)
+  FA_CASE(64)
+  FA_CASE(128)
+  FA_CASE(256)
+  FA_CASE(512)
+#undef FA_CASE
+  return fail(FA_ERR_UNSUPPORTED_D, "combine serves d in {32,64,128,256,512}");
+}
+
+int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int kv_per_split,
+                  int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (kv_per_split <= 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
+  const size_t need = fa_v2_workspace_bytes(B, H, L, d, kv_per_split);
+  if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(FA_ERR_WORKSPACE, "workspace must be 256-byte aligned and hold " + std::to_string(need) + " bytes");
+  const int ns = fa_v2_num_splits(L, kv_per_split);
+  const size_t rows = size_t(B) * H * L;
+  float* o_accum = static_cast<float*>(workspace);
+  float* lse_accum =
+      reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t(ns) * rows * d * sizeof(float)) + 255) & ~size_t(255)));
+  rc = fa_v2_splitkv_forward(Q, K, V, o_accum, lse_accum, B, H, L, d, kv_per_split, dtype, stream);
+  if (rc != FA_OK) return rc;
+  return fa_v2_combine(o_accum, lse_accum, O, B, H, L, d, ns, dtype, stream);
+}
+
+void fa_release_host_staging(void) {
+  std::lock_guard<std::mutex> lk(g_stage.mu);
+  for (auto& b : g_stage.buf) {
+    if (b) cudaFree(b);
+    b = nullptr;
+  }
+  if (g_stage.ws) cudaFree(g_stage.ws);
+  g_stage.ws = nullptr;
+  g_stage.bytes = g_stage.ws_bytes = 0;
+}
+
+int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh, void* Oh, int B, int H, int L, int d,
+                    int kv_per_split, int dtype) {
+  if (!Qh || !Kh || !Vh || !Oh) return fail(FA_ERR_ALIGN, "host pointers must be non-null");
+  if (B <= 0 || H <= 0 || L <= 0 || d <= 0) return fail(FA_ERR_SHAPE, "B, H, L, d must be positive");
+  if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F16) return fail(FA_ERR_DTYPE, "unknown dtype");
+  std::lock_guard<std::mutex> lk(g_stage.mu);
+  const size_t bytes = size_t(B) * H * L * d * elem_size(dtype);
+  if (bytes > g_stage.bytes) {
+    for (auto& b : g_stage.buf) {
+      if (b) cudaFree(b);
+      b = nullptr;
+    }
+    g_stage.bytes = 0;
+    for (auto& b : g_stage.buf) FA_CUDA_TRY(cudaMalloc(&b, bytes));
+    g_stage.bytes = bytes;
+  }
+  cudaStream_t s = nullptr;
+  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[0], Qh, bytes, cudaMemcpyHostToDevice, s));
+  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[1], Kh, bytes, cudaMemcpyHostToDevice, s));
+  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[2], Vh, bytes, cudaMemcpyHostToDevice, s));
+  int rc;
+  if (variant == 0) {
+    rc = fa_v1_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, dtype, s);
+  } else if (variant == 1) {
+    const int dt = d >= 64 ? 64 : d;
+    rc = fa_v1_tiled_d_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, dt, dt, dtype, s);
+  } else if (variant == 2) {
+    const size_t need = fa_v2_workspace_bytes(B, H, L, d, kv_per_split);
+    if (need == 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
+    if (need > g_stage.ws_bytes) {
+      if (g_stage.ws) cudaFree(g_stage.ws);
+      g_stage.ws = nullptr;
+      g_stage.ws_bytes = 0;
+      FA_CUDA_TRY(cudaMalloc(&g_stage.ws, need));
+      g_stage.ws_bytes = need;
+    }
+    rc = fa_v2_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, kv_per_split, dtype,
+                       g_stage.ws, g_stage.ws_bytes, s);
+  } else {
+    return fail(FA_ERR_SHAPE, "variant must be 0 (V1), 1 (tiled-d) or 2 (V2)");
+  }
+  if (rc != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(Oh, g_stage.buf[3], bytes, cudaMemcpyDeviceToHost, s));
+  FA_CUDA_TRY(cudaStreamSynchronize(s));
+  return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""Torch-facing wrappers over the C ABI: device tensors in, device tensors out, on the current stream.
+
+These are the B200 drop-ins for the reference host launchers
+(flash_attention_v1/CUDA/flash_attention_v1.h:251, flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:312,
+flash_attention_v2/CUDA/flash_attention_v2.h:438).  torch is used for memory, streams and nothing else.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.FA_DTYPE_F32, torch.bfloat16: _lib.FA_DTYPE_BF16, torch.float16: _lib.FA_DTYPE_F16}
+
+
+def _prep(Q, K, V):
+    if not (Q.is_cuda and K.is_cuda and V.is_cuda):
+        raise RuntimeError("flash-attention B200 path needs CUDA tensors: there is no CPU fallback")
+    if Q.dtype not in _DTYPES:
+        raise _lib.FlashAttentionError(-2, f"unsupported dtype {Q.dtype}")
+    if not (Q.dtype == K.dtype == V.dtype):
+        raise _lib.FlashAttentionError(-2, "Q, K, V must share a dtype")
+    if Q.dim() != 4 or Q.shape != K.shape or Q.shape != V.shape:
+        raise _lib.FlashAttentionError(-1, "Q, K, V must be [B,H,L,d] with identical shapes")
+    return Q.contiguous(), K.contiguous(), V.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def flash_attention_v1(Q, K, V, O=None, sync: bool = False):
+    """O = softmax(Q K^T / sqrt(d)) V for [B,H,L,d] tensors (fused-tile kernel, d <= 128)."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if O is None:
+        O = torch.empty_like(Q)
+    lib = _lib.load()
+    _lib.check(lib.fa_v1_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d, _DTYPES[Q.dtype],
+                                 _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return O
+
+
+def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: int = 32, sync: bool = False):
+    """Tiled-d variant (head dims up to 512); d_tile_* are validated streaming hints."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if O is None:
+        O = torch.empty_like(Q)
+    lib = _lib.load()
+    _lib.check(lib.fa_v1_tiled_d_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d,
+                                         d_tile_qk, d_tile_v, _DTYPES[Q.dtype], _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return O
+
+
+def v2_num_splits(L: int, kv_per_split: int) -> int:
+    return _lib.load().fa_v2_num_splits(L, kv_per_split)
+
+
+def v2_workspace(B, H, L, d, kv_per_split, device):
+    """Caller-owned workspace: (Oaccum [S,B*H,L,d] fp32, LSEaccum [S,B*H,L] fp32)."""
+    S = v2_num_splits(L, kv_per_split)
+    if S <= 0:
+        raise _lib.FlashAttentionError(-1, "kv_per_split must be positive")
+    return (torch.empty((S, B * H, L, d), dtype=torch.float32, device=device),
+            torch.empty((S, B * H, L), dtype=torch.float32, device=device))
+
+
+def flash_attention_v2_splitkv(Q, K, V, kv_per_split: int, Oaccum=None, LSEaccum=None):
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if Oaccum is None or LSEaccum is None:
+        Oaccum, LSEaccum = v2_workspace(B, H, L, d, kv_per_split, Q.device)
+    lib = _lib.load()
+    _lib.check(lib.fa_v2_splitkv_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), Oaccum.data_ptr(),
+                                         LSEaccum.data_ptr(), B, H, L, d, kv_per_split, _DTYPES[Q.dtype], _stream()))
+    return Oaccum, LSEaccum
+
+
+def flash_attention_v2_combine(Oaccum, LSEaccum, out_dtype, shape, O=None):
+    B, H, L, d = shape
+    S = Oaccum.shape[0]
+    if O is None:
+        O = torch.empty((B, H, L, d), dtype=out_dtype, device=Oaccum.device)
+    lib = _lib.load()
+    _lib.check(lib.fa_v2_combine(Oaccum.data_ptr(), LSEaccum.data_ptr(), O.data_ptr(), B, H, L, d, S,
+                                 _DTYPES[out_dtype], _stream()))
+    return O
+
+
+def flash_attention_v2(Q, K, V, kv_per_split: int, O=None, workspace=None, sync: bool = False):
+    """Split-KV forward + combine. `workspace` = (Oaccum, LSEaccum) from v2_workspace(), reused across calls."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if workspace is None:
+        workspace = v2_workspace(B, H, L, d, kv_per_split, Q.device)
+    Oaccum, LSEaccum = flash_attention_v2_splitkv(Q, K, V, kv_per_split, *workspace)
+    O = flash_attention_v2_combine(Oaccum, LSEaccum, Q.dtype, (B, H, L, d), O)
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return O
+
+
+def flash_attention_host(Qh, Kh, Vh, Oh=None, variant: int = 0, kv_per_split: int = 0):
+    """Host-buffer path (H2D x3 + kernel + D2H inside the library), like the reference drivers do around their
+    launchers (flash_attention_v1/CUDA/driver.cu:184-247). Tensors are CPU tensors, ideally pinned."""
+    if Qh.is_cuda:
+        raise RuntimeError("flash_attention_host takes host tensors")
+    B, H, L, d = Qh.shape
+    if Oh is None:
+        Oh = torch.empty_like(Qh).pin_memory()
+    lib = _lib.load()
+    _lib.check(lib.fa_forward_host(variant, Qh.data_ptr(), Kh.data_ptr(), Vh.data_ptr(), Oh.data_ptr(), B, H, L, d,
+                                   kv_per_split, _DTYPES[Qh.dtype]))
+    return Oh

@@ -1,0 +1,94 @@
+/* fa_b200.h — C ABI of libfa_b200.so, the B200 (sm_100a) flash-attention forward path.
+ *
+ * Every entry point is the drop-in for one host launcher of tyler-utah/exploring_flash_attention
+ * (paths below are relative to that repository).  Pointers are plain device (or, for the *_host
+ * variants, host) pointers to contiguous row-major [B,H,L,d] tensors, exactly the reference layout
+ * (base offset (b*H+h)*L*d, flash_attention_v1/CUDA/flash_attention_v1.h:182).  No torch types.
+ *
+ * Differences from the reference launchers, all deliberate:
+ *   - return an int status instead of assert()/void  (reference: flash_attention_v1.h:263-264);
+ *   - asynchronous on the caller's stream, no per-call cudaGetDeviceProperties / cudaDeviceSynchronize
+ *     (reference: flash_attention_v1.h:280-292);
+ *   - head dim and dtype are runtime arguments (reference: compile-time -DD, -DUSE_FP64);
+ *   - V2 workspace is caller-owned (reference cudaMalloc/cudaFree per call, flash_attention_v2.h:461-463,506-508);
+ *   - 64-bit element offsets.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef FA_B200_H
+#define FA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of Q, K, V, O */
+#define FA_DTYPE_F32 0  /* fp32 storage, tf32 tensor-core products, fp32 accumulation */
+#define FA_DTYPE_BF16 1 /* bf16 storage, fp32 accumulation */
+#define FA_DTYPE_F16 2  /* fp16 storage, fp32 accumulation (the reference's DATA_TYPE=__half) */
+
+/* status codes */
+#define FA_OK 0
+#define FA_ERR_SHAPE (-1)         /* non-positive B/H/L/d, bad tile hints */
+#define FA_ERR_DTYPE (-2)         /* unknown dtype */
+#define FA_ERR_ALIGN (-3)         /* base pointer not 16-byte aligned / NULL */
+#define FA_ERR_UNSUPPORTED_D (-4) /* head dim not served for this dtype */
+#define FA_ERR_CUDA (-5)          /* CUDA runtime / driver error, see fa_last_error() */
+#define FA_ERR_WORKSPACE (-6)     /* workspace too small */
+
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* fa_last_error(void);
+
+/* Library / device facts: returns sm count of the current device (<=0 on error). */
+int fa_device_sm_count(void);
+
+/* ---- V1 -------------------------------------------------------------------------------------
+ * Replaces  void flash_attention_v1(const DATA_TYPE* Q, K, V, DATA_TYPE* O, int B, int H, int L, int d_runtime)
+ *           flash_attention_v1/CUDA/flash_attention_v1.h:251-293  and  flash_attention_v1_opt1(...)
+ *           flash_attention_v1/CUDA/flash_attention_v1_opt1.h:354-396.
+ * d in {64,128} for 16-bit dtypes, {32,64} for FA_DTYPE_F32; larger d is served by fa_v1_tiled_d_forward. */
+int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int dtype,
+                  void* stream /* cudaStream_t */);
+
+/* ---- V1 tiled-d -----------------------------------------------------------------------------
+ * Replaces  void flash_attention_v1[_opt](..., int d_runtime, int d_tile_qk_runtime, int d_tile_v_runtime)
+ *           flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:312-354, flash_attention_v1_opt.h:448-490.
+ * d_tile_qk / d_tile_v are validated like the reference (positive, divide d) and are streaming-chunk
+ * hints: they change scheduling only, never results. */
+int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
+                          int d_tile_qk, int d_tile_v, int dtype, void* stream);
+
+/* ---- V2 split-KV ----------------------------------------------------------------------------
+ * Replaces  void flash_attention_v2(Q,K,V,O,B,H,L,d,d_tile_qk,d_tile_v,kv_tiles_per_block)
+ *           flash_attention_v2/CUDA/flash_attention_v2.h:438-509 (partial_attention_kernel :243-341,
+ *           reduction_kernel :356-435).
+ * A split covers kv_per_split consecutive keys (= BK_ref * kv_tiles_per_block in reference terms);
+ * n_splits = ceil(L / kv_per_split).  Workspace layout (split-major, fp32):
+ *   Oaccum   [n_splits][B*H][L][d]  each split normalised by its own l
+ *   LSEaccum [n_splits][B*H][L]     m/sqrt(d) + ln(l)
+ * which carries the same information as the reference's (O_unnormalised, m, l) triple
+ * (flash_attention_v2.h:321-340). */
+int fa_v2_num_splits(int L, int kv_per_split);
+size_t fa_v2_workspace_bytes(int B, int H, int L, int d, int kv_per_split);
+int fa_v2_splitkv_forward(const void* Q, const void* K, const void* V, float* Oaccum, float* LSEaccum, int B, int H,
+                          int L, int d, int kv_per_split, int dtype, void* stream);
+int fa_v2_combine(const float* Oaccum, const float* LSEaccum, void* O, int B, int H, int L, int d, int n_splits,
+                  int dtype, void* stream);
+/* split-KV + combine with a caller-owned workspace of at least fa_v2_workspace_bytes() bytes */
+int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int kv_per_split,
+                  int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer convenience (what the reference drivers do around their launchers:
+ * cudaMalloc + cudaMemcpy H2D x3 + launch + cudaMemcpy D2H, flash_attention_v1/CUDA/driver.cu:184-247).
+ * Q,K,V,O are HOST pointers (pinned for full PCIe speed); device staging buffers are cached inside the
+ * library between calls.  variant: 0 = V1, 1 = tiled-d, 2 = V2 (kv_per_split used).  Synchronous. */
+int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh, void* Oh, int B, int H, int L, int d,
+                    int kv_per_split, int dtype);
+void fa_release_host_staging(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H */

@@ -52,7 +52,7 @@ int elem_size(int dtype) { return dtype == FA_DTYPE_F32 ? 4 : 2; }
 
 // [BH][L][D] row-major tensor, box = one 128-byte-wide, `box_rows`-row block of one head, 128B swizzle.
 // Rows past L are zero-filled on load and clipped on store, so tiles never leak into the next head.
-int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows) {
+int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false) {
   EncodeFn enc = get_encode_fn();
   if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = elem_size(dtype);
@@ -63,8 +63,11 @@ int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, i
   cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(L) * D * es};
   cuuint32_t box[3] = {cuuint32_t(128 / es), cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // 32-bit MN-major UMMA operands (fp32 V) must use the 32B-atom flavour of the 128B swizzle.
+  const CUtensorMapSwizzle swz =
+      (mn_major_operand && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
   return FA_OK;
 }
@@ -88,7 +91,7 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   int rc;
   if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
   if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
   if (SPLIT) {
     tmO = tmQ;  // unused by the split epilogue
   } else if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) {

@@ -158,7 +158,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, D, 0, 1);
       constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);         // K-major, 8-row atoms 1024 B apart
-      constexpr uint64_t hiV = make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);  // MN-major: LBO = next 128-B column block
+      // MN-major V: LBO = next 128-B column block; 8-key atoms 1024 B apart.  32-bit (tf32) MN-major operands only
+      // exist in the 128B-swizzle / 32B-atom layout (4-key atoms, 512 B apart) — V's tensor map matches (fa_api.cu).
+      constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
+                                              : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
       const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
 
       auto qk = [&](int i, int stage) {  // S_i = Q_i K^T

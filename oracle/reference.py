@@ -1,0 +1,51 @@
+"""NumPy restatement of the reference oracle, common/reference.py:7-21 (naive_attention).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  `naive_attention` follows the reference line by line, including
+its dtype behaviour (Q @ K.T is evaluated in the input dtype, then promoted by the np.float64 scale — SURVEY.md
+§3.5).  The parity tests use `naive_attention_f64`, which up-casts the already-rounded inputs first so the
+oracle carries no rounding of its own.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def naive_attention(Q, K, V):
+    """softmax(Q K^T / sqrt(d)) V for one [L, d] head — common/reference.py:7-21."""
+    L, d = Q.shape
+    scale = 1.0 / np.sqrt(d)                               # reference.py:16
+    scores = (Q @ K.T) * scale                             # :17
+    scores = scores - scores.max(axis=1, keepdims=True)    # :18
+    probs = np.exp(scores)                                 # :19
+    probs = probs / probs.sum(axis=1, keepdims=True)       # :20
+    return probs @ V                                       # :21
+
+
+def naive_attention_f64(Q, K, V):
+    """Same math on float64 copies of the (already rounded) inputs. [L, d] -> [L, d] float64."""
+    return naive_attention(np.asarray(Q, dtype=np.float64), np.asarray(K, dtype=np.float64),
+                           np.asarray(V, dtype=np.float64))
+
+
+def naive_attention_batched_f64(Q, K, V, heads=None, rows=None):
+    """[B,H,L,d] (or [BH,L,d]) inputs -> float64 outputs for the selected flat head indices and query rows.
+
+    `rows` (slice or index array) limits the query rows so L=16384 stays tractable: only a [rows, L] score block is
+    ever materialised (common/reference.py materialises [L, L]).
+    """
+    Q = np.asarray(Q); K = np.asarray(K); V = np.asarray(V)
+    L, d = Q.shape[-2:]
+    Qf, Kf, Vf = (x.reshape(-1, L, d) for x in (Q, K, V))
+    heads = range(Qf.shape[0]) if heads is None else heads
+    rows = slice(None) if rows is None else rows
+    out = []
+    for h in heads:
+        q = Qf[h][rows].astype(np.float64)
+        k = Kf[h].astype(np.float64)
+        v = Vf[h].astype(np.float64)
+        s = (q @ k.T) * (1.0 / np.sqrt(d))
+        s -= s.max(axis=1, keepdims=True)
+        p = np.exp(s)
+        p /= p.sum(axis=1, keepdims=True)
+        out.append(p @ v)
+    return np.stack(out)

@@ -102,7 +102,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tc_fence_after();
     constexpr uint32_t idesc_pv = make_idesc(T::FMT, 128, D, 0, 1);
-    constexpr uint64_t hiV = make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
+    constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
+                                            : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
     for (int kk = 0; kk < 128 / UK; ++kk)
       umma_ts<T::KIND>(tb + 256, tb + kk * 8, make_smem_desc(smem_u32(sV) + kk * UK * 128, hiV), idesc_pv, kk > 0);
     tc_commit(&bars[2]);
@@ -186,8 +187,9 @@ int run(EncodeFn enc) {
     cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(128) * D * es};
     cuuint32_t box[3] = {cuuint32_t(128 / es), 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&maps[i], dt, 3, ptrs[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapSwizzle swz = (i == 2 && DT == DT_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(&maps[i], dt, 3, ptrs[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       printf("encode failed %d\n", int(r));
       return 2;

@@ -73,6 +73,18 @@ static inline void store_elem(void* p, size_t i, int dt, float v) {
   }
 }
 
+/* Row-wise softmax in place: max, exp, sum, normalise (standard.h:67-88). */
+static void softmax_rows(float* scores, int L) {
+  for (int i = 0; i < L; ++i) {
+    float* row = scores + (size_t)i * L;
+    float mx = row[0];
+    for (int j = 1; j < L; ++j) if (row[j] > mx) mx = row[j];
+    float sum = 0.0f;
+    for (int j = 0; j < L; ++j) { row[j] = expf(row[j] - mx); sum += row[j]; }
+    for (int j = 0; j < L; ++j) row[j] /= sum;
+  }
+}
+
 /* Heads [head_begin, head_end) of the flattened B*H axis are computed (a bounded sample for the CPU baseline);
  * pass 0, B*H for the whole tensor.  Returns 0, or -1 on bad arguments / allocation failure. */
 int oracle_standard_attention_cpu(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
@@ -88,8 +100,30 @@ int oracle_standard_attention_cpu(const void* Q, const void* K, const void* V, v
   for (int bh = head_begin; bh < head_end; ++bh) {                              /* :41-43 */
     const size_t base = (size_t)bh * L * d;                                     /* :46 */
     float* scores = (float*)malloc((size_t)L * L * sizeof(float));              /* :52 */
+    if (!scores) { failed = 1; continue; }
+    if (dtype == 3) {
+      /* USE_FP64=1: DATA_TO_FLOAT is the identity, so each product is formed in double and added to the float
+       * accumulator in double before rounding back to float (standard.h:58-62, :93-97). */
+      const double* q = (const double*)Q + base; const double* k = (const double*)K + base;
+      const double* v = (const double*)V + base; double* o = (double*)O + base;
+      for (int i = 0; i < L; ++i)
+        for (int j = 0; j < L; ++j) {
+          float sum = 0.0f;
+          for (int c = 0; c < d; ++c) sum = (float)((double)sum + q[(size_t)i * d + c] * k[(size_t)j * d + c]);
+          scores[(size_t)i * L + j] = sum * scale;
+        }
+      softmax_rows(scores, L);
+      for (int i = 0; i < L; ++i)
+        for (int c = 0; c < d; ++c) {
+          float sum = 0.0f;
+          for (int j = 0; j < L; ++j) sum = (float)((double)sum + (double)scores[(size_t)i * L + j] * v[(size_t)j * d + c]);
+          o[(size_t)i * d + c] = (double)sum;
+        }
+      free(scores);
+      continue;
+    }
     float* q = (float*)malloc((size_t)L * d * sizeof(float) * 3);
-    if (!scores || !q) { failed = 1; free(scores); free(q); continue; }
+    if (!q) { failed = 1; free(scores); continue; }
     float* k = q + (size_t)L * d; float* v = k + (size_t)L * d;
     for (size_t i = 0; i < (size_t)L * d; ++i) {                                /* DATA_TO_FLOAT hoisted out of the loops */
       q[i] = load_elem(Q, base + i, dtype); k[i] = load_elem(K, base + i, dtype); v[i] = load_elem(V, base + i, dtype);
@@ -100,14 +134,7 @@ int oracle_standard_attention_cpu(const void* Q, const void* K, const void* V, v
         for (int c = 0; c < d; ++c) sum += q[(size_t)i * d + c] * k[(size_t)j * d + c];
         scores[(size_t)i * L + j] = sum * scale;
       }
-    for (int i = 0; i < L; ++i) {                                               /* :67-88 */
-      float* row = scores + (size_t)i * L;
-      float mx = row[0];
-      for (int j = 1; j < L; ++j) if (row[j] > mx) mx = row[j];
-      float sum = 0.0f;
-      for (int j = 0; j < L; ++j) { row[j] = expf(row[j] - mx); sum += row[j]; }
-      for (int j = 0; j < L; ++j) row[j] /= sum;
-    }
+    softmax_rows(scores, L);                                                    /* :67-88 */
     for (int i = 0; i < L; ++i)                                                 /* :91-99 */
       for (int c = 0; c < d; ++c) {
         float sum = 0.0f;

@@ -136,9 +136,16 @@ template <int D, int DT>
 int launch_combine(const float* o_accum, const float* lse_accum, void* O, long long rows, int n_splits,
                    cudaStream_t s) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;
-  constexpr int RPB = fa::kCombineThreads / G;
-  const long long blocks = (rows + RPB - 1) / RPB;
-  fa::fa_combine_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
+  constexpr int NV = D / (4 * G);
+  if (n_splits <= fa::kCombineMaxSplitsFast) {
+    constexpr int RPB = (fa::kCombineThreads / G) * ((NV >= 2) ? 1 : 2);
+    const long long blocks = (rows + RPB - 1) / RPB;
+    fa::fa_combine_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
+  } else {
+    constexpr int RPB = fa::kCombineThreads / G;
+    const long long blocks = (rows + RPB - 1) / RPB;
+    fa::fa_combine_generic_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
+  }
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }

@@ -51,13 +51,128 @@ __device__ __forceinline__ void store_out4(void* O, size_t elem_idx, float4 v) {
 }
 
 constexpr int kCombineThreads = 256;
-constexpr int kCombineMaxUnroll = 8;  // splits kept in flight per thread
+constexpr int kCombineMaxUnroll = 8;  // generic kernel: splits kept in flight per thread
+constexpr int kCombineChunk = 4;      // fast kernel: splits loaded per batch
+constexpr int kCombineMaxSplitsFast = 32;
 
-// D: head dim (multiple of 4).  One lane group of G lanes per row; NV float4 vectors per lane.
+// Fast path (n_splits <= 32).  A group of G = min(32, D/4) lanes owns RPT query rows (interleaved so that adjacent
+// groups touch adjacent rows); lane gl of a group owns split gl's LSE (+G, +2G.. for small D), so
+//   LSE_max / sum exp  are xor-shuffle reductions inside the group, and weight w_k is fetched with one shuffle.
+// Every global load of a batch — the LSE words and RPT*4*NV 16-byte Oaccum vectors — is issued before the first
+// dependent instruction, so one memory round trip covers both the softmax-over-splits and the first 4 splits.
 template <int D, int DT>
 __global__ void __launch_bounds__(kCombineThreads)
 fa_combine_kernel(const float* __restrict__ o_accum, const float* __restrict__ lse_accum, void* __restrict__ O,
                   long long rows, int n_splits) {
+  constexpr int G = (D / 4 < 32) ? D / 4 : 32;
+  constexpr int NV = D / (4 * G);
+  constexpr int KK = kCombineMaxSplitsFast / G;          // LSE slots per lane
+  constexpr int RPT = (NV >= 2) ? 1 : 2;                 // rows per lane group
+  constexpr int GROUPS = kCombineThreads / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int gbase = lane & ~(G - 1);
+  const long long row0 = (long long)blockIdx.x * (GROUPS * RPT) + threadIdx.x / G;
+  const size_t split_stride = size_t(rows) * D;
+
+  long long r[RPT];
+  bool live[RPT];
+#pragma unroll
+  for (int t = 0; t < RPT; ++t) {
+    const long long row = row0 + (long long)t * GROUPS;
+    live[t] = row < rows;
+    r[t] = live[t] ? row : rows - 1;  // dead groups shadow the last row so whole warps stay converged for the shuffles
+  }
+
+  // ---- issue: LSE words first (they come back first), then the first batch of Oaccum vectors
+  float e[RPT][KK];
+#pragma unroll
+  for (int t = 0; t < RPT; ++t)
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const int k = kk * G + gl;
+      e[t][kk] = (k < n_splits) ? __ldg(lse_accum + size_t(k) * rows + r[t]) : -CUDART_INF_F;
+    }
+  float4 x[RPT][kCombineChunk][NV];
+  auto issue = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < RPT; ++t)
+#pragma unroll
+      for (int u = 0; u < kCombineChunk; ++u)
+        if (k0 + u < n_splits) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            x[t][u][v] = ld_stream_f4(o_accum + size_t(k0 + u) * split_stride + size_t(r[t]) * D + v * (G * 4) + gl * 4);
+        }
+  };
+  issue(0);
+
+  // ---- softmax over splits (per row): w_k = exp(LSE_k - max) / sum, kept by the lane that owns split k
+  float w[RPT][KK];
+#pragma unroll
+  for (int t = 0; t < RPT; ++t) {
+    float mx = e[t][0];
+#pragma unroll
+    for (int kk = 1; kk < KK; ++kk) mx = fmaxf(mx, e[t][kk]);
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      w[t][kk] = __expf(e[t][kk] - mx);  // exp(-inf) = 0 for the unused slots
+      sum += w[t][kk];
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) w[t][kk] *= inv;
+  }
+
+  float4 acc[RPT][NV];
+#pragma unroll
+  for (int t = 0; t < RPT; ++t)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[t][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+    for (int j0 = 0; j0 < G; j0 += kCombineChunk) {
+      const int k0 = kk * G + j0;
+      if (k0 >= n_splits) break;
+      if (k0 > 0) issue(k0);
+#pragma unroll
+      for (int u = 0; u < kCombineChunk; ++u) {
+#pragma unroll
+        for (int t = 0; t < RPT; ++t) {
+          const float wk = __shfl_sync(0xffffffffu, w[t][kk], gbase + ((j0 + u) & (G - 1)));
+          if (k0 + u < n_splits) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              acc[t][v].x = fmaf(wk, x[t][u][v].x, acc[t][v].x);
+              acc[t][v].y = fmaf(wk, x[t][u][v].y, acc[t][v].y);
+              acc[t][v].z = fmaf(wk, x[t][u][v].z, acc[t][v].z);
+              acc[t][v].w = fmaf(wk, x[t][u][v].w, acc[t][v].w);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < RPT; ++t)
+    if (live[t]) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        store_out4<DT>(O, size_t(row0 + (long long)t * GROUPS) * D + v * (G * 4) + gl * 4, acc[t][v]);
+    }
+}
+
+// Generic path (any n_splits): same data movement, LSE re-read per split instead of kept in lane slots.
+template <int D, int DT>
+__global__ void __launch_bounds__(kCombineThreads)
+fa_combine_generic_kernel(const float* __restrict__ o_accum, const float* __restrict__ lse_accum, void* __restrict__ O,
+                          long long rows, int n_splits) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;
   constexpr int NV = D / (4 * G);
   constexpr int ROWS_PER_BLOCK = kCombineThreads / G;

@@ -133,6 +133,42 @@ int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, i
 }
 
 template <int D, int DT>
+int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream) {
+  using T = fa::TiledDTraits<D, DT>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
+  if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) return rc;
+  fa::FwdParams p;
+  p.L = L;
+  p.BH = BH;
+  p.kv_per_split = L;
+  p.n_splits = 1;
+  p.scale = 1.0f / std::sqrt(float(D));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.o_accum = nullptr;
+  p.lse_accum = nullptr;
+  auto kern = fa::fa_tiled_d_kernel<D, DT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  dim3 grid((L + 127) / 128, BH, T::NSLAB);
+  kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
+                     cudaStream_t s) {
+  if (d == 256 && dtype == fa::DT_BF16) return launch_tiled_d<256, fa::DT_BF16>(Q, K, V, O, BH, L, s);
+  if (d == 512 && dtype == fa::DT_BF16) return launch_tiled_d<512, fa::DT_BF16>(Q, K, V, O, BH, L, s);
+  if (d == 256 && dtype == fa::DT_F16) return launch_tiled_d<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
+  if (d == 512 && dtype == fa::DT_F16) return launch_tiled_d<512, fa::DT_F16>(Q, K, V, O, BH, L, s);
+  return fail(FA_ERR_UNSUPPORTED_D, "tiled-d kernel serves d in {256,512} for bf16/fp16; got d=" + std::to_string(d) +
+                                        " dtype=" + std::to_string(dtype));
+}
+
+template <int D, int DT>
 int launch_combine(const float* o_accum, const float* lse_accum, void* O, long long rows, int n_splits,
                    cudaStream_t s) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;
@@ -189,7 +225,7 @@ int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, 
     return fail(FA_ERR_SHAPE, "d_tile_qk and d_tile_v must be positive divisors of d");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d <= 128) return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
-  return fa::tiled_d_dispatch(Q, K, V, O, B * H, L, d, dtype, s, &g_err);
+  return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, s);
 }
 
 int fa_v2_num_splits(int L, int kv_per_split) {

@@ -1,11 +1,308 @@
-// fa_tiled_d_sm100.cuh — K2 placeholder (filled in below in this round): head dims 256 / 512.
+// fa_tiled_d_sm100.cuh — K2: tiled-d flash-attention forward for head dims 256 and 512 (16-bit storage).
+//
+// Replaces, for d > 128 (same semantics, [B,H,L,d] contiguous, dense, scale 1/sqrt(d)):
+//   flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:230-309      flash_attention_kernel (scalar, O in fp32 regs)
+//   flash_attention_v1_tiled_d/CUDA/flash_attention_v1_opt.h:366-445  flash_attention_kernel_opt (WMMA)
+// and follows the same two d-loops: QK^T accumulates S over d_tile_qk-wide chunks of Q and K
+// (flash_attention_v1.h:154-178, numpy_gpu_like.py:40-62) and S.V produces O one d_tile_v-wide column slab at a time
+// (flash_attention_v1.h:209-226, numpy_gpu_like.py:89-105).  The reference re-reads the Q chunk from global memory
+// for every KV tile (:158-164); here Q stays resident in shared memory and only K / V chunks stream.
+//
+// B200 mapping (why this is a different kernel from K1): a 128-row O accumulator at d = 512 would need all 512 TMEM
+// columns, leaving nothing for S.  So one CTA owns 128 query rows x one 256-wide slab of the output head dim:
+//   TMEM  S[0] [0,128)  S[1] [128,256)  O [256,512)            (S double-buffered: QK(j+1) overlaps softmax(j))
+//   grid  (ceil(L/128), B*H, D/256);  for d = 512 the two slabs of a q-tile recompute S (QK^T is 2/3 of the MMA work
+//         there; documented cost of fitting TMEM — the roofline uses algorithmic FLOPs only).
+//   smem  Q resident as D/64 swizzled [128 x 128 B] blocks; one ring of 16 KB stages streams, per KV tile,
+//         D/64 K chunks ([128 keys x 64 d], K-major B operand) then 4 V chunks ([128 keys x 64 d_v], MN-major B operand).
+//   warps 0-3 softmax (thread <-> row), 4 TMA producer, 5 MMA issuer.
 #pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
 #include <string>
+
 #include "fa_fwd_sm100.cuh"
+
 namespace fa {
-inline int tiled_d_dispatch(const void*, const void*, const void*, void*, int, int, int d, int, cudaStream_t,
-                            std::string* err) {
-  *err = "tiled-d kernel for d=" + std::to_string(d) + " not built";
-  return -4;
+
+template <int D, int DT>
+struct TiledDTraits {
+  static_assert(DT != DT_F32, "tiled-d kernel is 16-bit storage only");
+  static_assert(D == 256 || D == 512, "tiled-d kernel serves d = 256, 512");
+  static constexpr uint32_t FMT = (DT == DT_BF16) ? FMT_BF16 : FMT_F16;
+  static constexpr int BM = 128, BN = 128;
+  static constexpr int CH = 64;                         // head-dim chunk (elements) = one 128-byte swizzle row
+  static constexpr int BLK_BYTES = 128 * 128;           // one chunk block: 128 rows x 128 B
+  static constexpr int NKC = D / CH;                    // K (and Q) chunks per tile
+  static constexpr int DV = 256;                        // output columns owned by one CTA
+  static constexpr int NVC = DV / CH;                   // V chunks per tile
+  static constexpr int NSLAB = D / DV;
+  static constexpr int Q_BYTES = NKC * BLK_BYTES;
+  static constexpr int NS = (227 * 1024 - 2048 - Q_BYTES) / BLK_BYTES;   // ring depth: 6 (d=512), 10 (d=256)
+  static constexpr int NUM_BARS = 1 + 2 * NS + 2 + 2 + 1;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + NS * BLK_BYTES + NUM_BARS * 8 + 16;
+  static constexpr int THREADS = 256;
+  static constexpr int TM_S = 0, TM_O = 256;
+};
+
+template <int D, int DT>
+__global__ void __launch_bounds__(256, 1)
+fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
+  using T = TiledDTraits<D, DT>;
+  constexpr int BM = T::BM, BN = T::BN, CH = T::CH, BLK_BYTES = T::BLK_BYTES, NKC = T::NKC, NVC = T::NVC, NS = T::NS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sRing = smem + T::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NS * BLK_BYTES);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* full = q_full + 1;        // [NS] TMA -> MMA
+  uint64_t* empty = full + NS;        // [NS] MMA (tcgen05.commit) -> TMA
+  uint64_t* s_full = empty + NS;      // [2]  MMA -> softmax: S[b] holds tile j (b = j & 1)
+  uint64_t* p_full = s_full + 2;      // [2]  softmax (128 arrivals) -> MMA: P[b] written, O rescaled
+  uint64_t* pv_done = p_full + 2;     // [1]  MMA -> softmax: PV(j) retired (phase j)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_row0 = blockIdx.x * BM;
+  const int bh = blockIdx.y;
+  const int slab = blockIdx.z;                 // which 256-wide slab of the output head dim
+  const int n_tiles = (p.L + BN - 1) / BN;
+
+  if (warp == 5 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 128);
+    }
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmO);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, T::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < NKC; ++c) tma_load_3d(sQ + c * BLK_BYTES, &tmQ, q_full, c * CH, q_row0, bh);
+      int it = 0;
+      auto load_chunk = [&](const CUtensorMap* map, int col, int row) {
+        const int stage = it % NS;
+        if (it >= NS) mbar_wait(&empty[stage], ((it / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&full[stage], BLK_BYTES);
+        tma_load_3d(sRing + stage * BLK_BYTES, map, &full[stage], col, row, bh);
+        ++it;
+      };
+      // consumption order: K(0) | K(1) V(0) | K(2) V(1) | ... | V(n-1)
+      for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles)
+          for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, (j + 1) * BN);
+        for (int v = 0; v < NVC; ++v) load_chunk(&tmV, slab * T::DV + v * CH, j * BN);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, CH, 0, 1);
+      constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);
+      constexpr uint64_t hiV = make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
+      const uint32_t sQ_addr = smem_u32(sQ), ring_addr = smem_u32(sRing);
+      int it = 0;
+      auto qk = [&](int b) {  // S[b] = Q K^T, accumulated over the d chunks as they land
+        for (int c = 0; c < NKC; ++c) {
+          const int stage = it % NS;
+          mbar_wait(&full[stage], (it / NS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < CH / 16; ++k)
+            umma_ss<KIND_F16>(tmem_base + T::TM_S + b * BN, make_smem_desc(sQ_addr + c * BLK_BYTES + k * 32, hiK),
+                              make_smem_desc(ring_addr + stage * BLK_BYTES + k * 32, hiK), idesc_qk, (c | k) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          ++it;
+        }
+        tc_commit(&s_full[b]);
+      };
+      auto pv = [&](int b, uint32_t acc) {  // O[:, 64v..64v+63] (+)= P[b] V_chunk(v)
+        for (int v = 0; v < NVC; ++v) {
+          const int stage = it % NS;
+          mbar_wait(&full[stage], (it / NS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk)
+            umma_ts<KIND_F16>(tmem_base + T::TM_O + v * CH, tmem_base + T::TM_S + b * BN + kk * 8,
+                              make_smem_desc(ring_addr + stage * BLK_BYTES + kk * 16 * 128, hiV), idesc_pv,
+                              (acc | (kk > 0)) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          ++it;
+        }
+        tc_commit(pv_done);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) qk((j + 1) & 1);      // overlaps softmax(j); in-order after PV(j-1), which read P[(j+1)&1]
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        pv(j & 1, j > 0 ? 1u : 0u);
+      }
+    }
+  } else if (warp < 4) {
+    // ===================================== softmax warpgroup ==================================
+    const int row = warp * 32 + lane;
+    const uint32_t t_lane = tmem_base + (uint32_t(warp * 32) << 16);
+    const uint32_t tO = t_lane + T::TM_O;
+    float m_used = -CUDART_INF_F;
+    float l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t tS = t_lane + T::TM_S + (j & 1) * BN;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+      tc_wait_ld();
+
+      const int valid = p.L - j * BN;
+      if (valid < BN) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int x = 0; x < 32; ++x)
+            if (c * 32 + x >= valid) s[c][x] = __float_as_uint(-CUDART_INF_F);
+      }
+      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+      for (int x = 0; x < 32; ++x) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[1][x]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // PV(j-1) was issued after QK(j), so S-ready does not cover it here: wait for its own commit (phase j-1).
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
+          if (need) m_used = mx;
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < T::DV / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+            tmem_st32(tO + c * 32, o);
+          }
+        }
+      }
+
+      const float neg_m = -m_used * p.scale_log2;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int x = 0; x < 32; ++x) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[0][x]), p.scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[1][x]), p.scale_log2, neg_m));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(s[2][x]), p.scale_log2, neg_m));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(s[3][x]), p.scale_log2, neg_m));
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        s[0][x] = __float_as_uint(p0);
+        s[1][x] = __float_as_uint(p1);
+        s[2][x] = __float_as_uint(p2);
+        s[3][x] = __float_as_uint(p3);
+      }
+      l += (l0 + l1) + (l2 + l3);
+      uint32_t pk[2][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float a = __uint_as_float(s[c][2 * x]), b = __uint_as_float(s[c][2 * x + 1]);
+          pk[c >> 1][(c & 1) * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+        }
+      tmem_st32(tS, pk[0]);
+      tmem_st32(tS + 32, pk[1]);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[j & 1]);
+    }
+
+    // ------------------------------- epilogue: O / l -> bf16/fp16 -> smem (Q's dead blocks) -> TMA store ---------
+    // A parity wait can only tell "phase x done" from "phase x running": PV(n-2) may still be in flight here (it was
+    // issued after QK(n-1)), so step through phase n-2 first, then the last one.
+    if (n_tiles >= 2) mbar_wait(pv_done, (n_tiles - 2) & 1);
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int c = 0; c < T::DV / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tc_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // 4 x 16-byte chunks per 32 columns
+        auto pk2 = [&](int e) {
+          const float a = __uint_as_float(o[e]) * inv_l, b = __uint_as_float(o[e + 1]) * inv_l;
+          return (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+        };
+        uint4 v;
+        v.x = pk2(8 * u + 0);
+        v.y = pk2(8 * u + 2);
+        v.z = pk2(8 * u + 4);
+        v.w = pk2(8 * u + 6);
+        const int q = c * 4 + u;  // 16-byte chunk index within the 512-byte slab row
+        uint8_t* dst = sQ + (q >> 3) * BLK_BYTES + row * 128 + (((q & 7) ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+      for (int b = 0; b < NVC; ++b) tma_store_3d(&tmO, sQ + b * BLK_BYTES, slab * T::DV + b * CH, q_row0, bh);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
+
+// Host-side dispatch lives in fa_api.cu (tensor maps); this helper only reports the supported set.
+inline bool tiled_d_supported(int d, int dtype) { return (d == 256 || d == 512) && (dtype == DT_BF16 || dtype == DT_F16); }
+
 }  // namespace fa

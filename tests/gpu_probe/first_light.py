@@ -33,6 +33,10 @@ CASES = [
     ("C1_full", "v1", 32, 8, 1024, 32, "f32", 0),
     ("C3_full", "v2", 32, 8, 256, 64, "bf16", 64),
     ("C4_slice", "v1", 1, 16, 16384, 128, "bf16", 0),
+    ("td_d256", "v1", 1, 2, 512, 256, "bf16", 0),
+    ("td_d512", "v1", 1, 2, 512, 512, "bf16", 0),
+    ("td_d256_big", "v1", 4, 8, 4096, 256, "bf16", 0),
+    ("C5_full", "v1", 16, 8, 4096, 512, "bf16", 0),
 ]
 
 

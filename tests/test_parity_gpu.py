@@ -66,6 +66,49 @@ def test_v1_matches_oracle(ops, B, H, L, d, dtype):
     assert torch.equal(O, O2)      # d-chunk hints change scheduling only
 
 
+@pytest.mark.parametrize("B,H,L,d,dtype", [
+    (1, 2, 256, 256, torch.bfloat16), (1, 2, 384, 512, torch.bfloat16), (1, 1, 512, 512, torch.float16),
+    (1, 2, 333, 512, torch.bfloat16), (1, 1, 100, 256, torch.float16), (2, 1, 129, 512, torch.bfloat16),
+    (1, 1, 1, 512, torch.bfloat16),
+])
+def test_tiled_d_large_head_dims_match_oracle(ops, B, H, L, d, dtype):
+    """K2: d = 256 / 512 (TMEM holds one 256-wide O slab per CTA); d_tile hints are validated like the reference."""
+    from exploring_flash_attention_b200 import FlashAttentionError
+    Q, K, V = uniform_qkv(B, H, L, d, dtype)
+    O = ops.flash_attention_v1_tiled_d(Q, K, V, d_tile_qk=32, d_tile_v=32, sync=True)
+    assert not torch.isnan(O).any()
+    assert max_err(O, oracle_out(Q, K, V)) <= TOL[dtype]
+    assert torch.equal(O, ops.flash_attention_v1(Q, K, V, sync=True))          # V1 entry point routes d > 128 here
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_v1_tiled_d(Q, K, V, d_tile_qk=48, d_tile_v=32)      # must divide d
+
+
+def test_tiled_d_rescale_path(ops):
+    B, H, L, d = 1, 1, 640, 512
+    Q, K, V = uniform_qkv(B, H, L, d, torch.bfloat16)
+    ramp = torch.linspace(0.3, 8.0, L, device="cuda").view(1, 1, L, 1)
+    K = (K.float() * ramp).bfloat16()
+    O = ops.flash_attention_v1_tiled_d(Q, K, V, sync=True)
+    ref = oracle_out(Q, K, V)
+    assert not torch.isnan(O).any()
+    assert max_err(O, ref) <= 2e-3 * max(1.0, np.abs(ref).max()) * 4
+
+
+def test_c5_full_size_sampled(ops):
+    """BASELINE.json configs[4]: B16 H8 L4096 d512 bf16 — sampled oracle rows + softmax-rows-sum-to-one."""
+    B, H, L, d = 16, 8, 4096, 512
+    g = torch.Generator(device="cpu").manual_seed(42)
+    base = [((torch.rand((1, H, L, d), generator=g) * 2 - 1)).bfloat16().cuda() for _ in range(3)]
+    Q, K, V = (x.expand(B, H, L, d).contiguous() for x in base)
+    Q[1:] = Q[1:].roll(1, dims=2)                                               # make batches differ
+    O = ops.flash_attention_v1_tiled_d(Q, K, V, sync=True)
+    heads = [0, 77, B * H - 1]
+    rows = np.r_[0:32, L // 2:L // 2 + 32, L - 32:L]
+    assert max_err(O, oracle_out(Q, K, V, heads=heads, rows=rows), heads=heads, rows=rows) <= 2e-3
+    ones = torch.ones_like(V)
+    assert (ops.flash_attention_v1_tiled_d(Q, K, ones, sync=True).float() - 1).abs().max().item() <= 4e-3
+
+
 @pytest.mark.parametrize("B,H,L,d,dtype,kvs", [
     (4, 8, 256, 64, torch.bfloat16, 64),       # C3 geometry: 4 splits of 64 keys
     (1, 4, 1024, 128, torch.bfloat16, 256), (1, 2, 500, 32, torch.float32, 96), (1, 2, 300, 64, torch.float16, 300),

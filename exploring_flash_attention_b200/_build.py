@@ -10,7 +10,8 @@ import subprocess
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libfa_b200.so"
+# FA_B200_LIB lets a developer point the loader at an alternative build (A/B experiments); default is the in-tree .so
+LIB_PATH = Path(os.environ["FA_B200_LIB"]) if os.environ.get("FA_B200_LIB") else CSRC / "libfa_b200.so"
 SOURCES = ["fa_api.cu"]
 HEADERS = ["sm100_ptx.cuh", "fa_fwd_sm100.cuh", "fa_tiled_d_sm100.cuh", "fa_combine_sm100.cuh",
            "../../include/fa_b200.h"]
@@ -34,11 +35,13 @@ def is_stale() -> bool:
     return any((CSRC / f).stat().st_mtime > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the library if missing or older than its sources. Returns the .so path."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
+    """Compile the library if missing or older than its sources. Returns the .so path.
+    `defines` / `out` build a tuning variant (e.g. defines=("FA_P_HALVES=1",), out=Path("/tmp/x.so"))."""
+    target = Path(out) if out else LIB_PATH
+    if not force and not defines and out is None and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(target), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -47,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

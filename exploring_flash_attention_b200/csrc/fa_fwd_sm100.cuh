@@ -136,7 +136,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int row) {
         mbar_arrive_expect_tx(bar, TILE_BYTES);
 #pragma unroll
@@ -154,7 +154,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, D, 0, 1);
       constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);         // K-major, 8-row atoms 1024 B apart

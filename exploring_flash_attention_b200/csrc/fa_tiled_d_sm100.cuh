@@ -103,7 +103,7 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   if (warp == 4) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, T::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < NKC; ++c) tma_load_3d(sQ + c * BLK_BYTES, &tmQ, q_full, c * CH, q_row0, bh);
@@ -125,7 +125,7 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 5) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, CH, 0, 1);
       constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);

@@ -25,6 +25,20 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync tells the compiler exactly one thread runs the
+// guarded code, so warp-uniform operands of tcgen05.mma / TMA go to uniform registers with a plain R2UR instead of a
+// per-instruction "waterfall" loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) — measured: ~110 -> ~10 cycles per MMA issue.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

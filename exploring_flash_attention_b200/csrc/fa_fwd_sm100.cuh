@@ -60,10 +60,18 @@ struct FwdTraits {
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S = 0, TM_O = 256;
   static_assert(256 + 2 * D <= 512, "S and O accumulators must fit TMEM");
-  static constexpr int NUM_BARS = 2 + 2 * NS + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 2 + 2 * NS + 2 + 4 + 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + NUM_BARS * 8 + 16;
   static constexpr int THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle}
 };
+
+// Tuning knobs (A/B-tested on B200 through alternative builds; the defaults are what ships).
+#ifndef FA_P_HALVES
+#define FA_P_HALVES 1   // 1: publish P in two 64-key halves so the first half of PV overlaps the second half of exp
+#endif
+#ifndef FA_PACKED
+#define FA_PACKED 1     // 1: packed fp32x2 FFMA2 / FADD2 for the scale-subtract and the row sum (halves their issue slots)
+#endif
 
 // Softmax rescale threshold in log2 units (P values stay <= 2^8; exact after the final O / l).
 constexpr float kRescaleThreshold = 8.0f;
@@ -86,8 +94,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* kv_full = q_full + 2;       // [NS] TMA -> MMA
   uint64_t* kv_empty = kv_full + NS;    // [NS] MMA (tcgen05.commit) -> TMA
   uint64_t* s_full = kv_empty + NS;     // [2]  MMA -> softmax: S_i(j) ready (and every earlier MMA retired)
-  uint64_t* p_full = s_full + 2;        // [2]  softmax (128 arrivals) -> MMA: P_i(j) in TMEM, O_i rescaled
-  uint64_t* o_done = p_full + 2;        // [2]  MMA -> softmax: last PV_i retired
+  uint64_t* p_full = s_full + 2;        // [2][2] softmax (128 arrivals) -> MMA: P_i(j) (key half h) in TMEM, O_i rescaled
+  uint64_t* o_done = p_full + 4;        // [2]  MMA -> softmax: last PV_i retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -109,7 +117,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[2 * i], 128);
+      mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
     }
     fence_mbar_init();
@@ -173,10 +182,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         make_smem_desc(b_base + off, hiK), idesc_qk, k > 0 ? 1u : 0u);
         }
       };
-      auto pv = [&](int i, int stage, uint32_t acc) {  // O_i (+)= P_i V
+      auto pv = [&](int i, int stage, uint32_t acc, int kk0, int kk1) {  // O_i (+)= P_i V  (K-steps kk0..kk1-1)
         const uint32_t b_base = sKV_addr + stage * TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BN / UK; ++kk) {
+        for (int kk = kk0; kk < kk1; ++kk) {
           umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_S + i * BN + kk * 8,
                         make_smem_desc(b_base + kk * UK * 128, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
         }
@@ -195,9 +204,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const bool has_next = (j + 1 < n_tiles);
         mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
         for (int i = 0; i < n_q; ++i) {
-          mbar_wait(&p_full[i], j & 1);
+          constexpr int KT = BN / UK;
+          mbar_wait(&p_full[2 * i], j & 1);
           tc_fence_after();
-          pv(i, tv % NS, j > 0 ? 1u : 0u);
+          if (FA_P_HALVES) {
+            pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+            mbar_wait(&p_full[2 * i + 1], j & 1);
+            tc_fence_after();
+            pv(i, tv % NS, 1u, KT / 2, KT);
+          } else {
+            pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
+          }
           if (!has_next) tc_commit(&o_done[i]);
           if (has_next) {
             if (i == 0) {
@@ -233,22 +250,32 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
         tc_wait_ld();
 
+        // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
+        // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
         const int valid = kv_end - (kv_begin + j * BN);
-        if (valid < BN) {
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+        if (valid >= BN) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[1][x]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
+            mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
+          }
+        } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int x = 0; x < 32; ++x)
               if (c * 32 + x >= valid) s[c][x] = __float_as_uint(-CUDART_INF_F);
-        }
-
-        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[1][x]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
+          for (int x = 0; x < 32; ++x) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[1][x]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
+            mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
+          }
+          asm volatile("" ::: "memory");  // keep this a real branch
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
@@ -275,39 +302,71 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
 
         const float neg_m = -m_used * p.scale_log2;
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        // p = 2^(s*scale_log2 - m*scale_log2): column blocks c0..c1-1 of s, four independent streams per step
+        float2 lsum[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+        auto exp_blocks = [&](int c0, int c1) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[0][x]), p.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[1][x]), p.scale_log2, neg_m));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(s[2][x]), p.scale_log2, neg_m));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(s[3][x]), p.scale_log2, neg_m));
-          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-          s[0][x] = __float_as_uint(p0);
-          s[1][x] = __float_as_uint(p1);
-          s[2][x] = __float_as_uint(p2);
-          s[3][x] = __float_as_uint(p3);
-        }
-        l += (l0 + l1) + (l2 + l3);
-
-        if constexpr (DT == DT_F32) {
+          for (int x = 0; x < 32; x += 2) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_st32(tS + c * 32, s[c]);
-        } else {
-          uint32_t pk[2][32];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int x = 0; x < 16; ++x) {
-              const float a = __uint_as_float(s[c][2 * x]), b = __uint_as_float(s[c][2 * x + 1]);
-              pk[c >> 1][(c & 1) * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+            for (int c = c0; c < c1; ++c) {
+              float2 v = make_float2(__uint_as_float(s[c][x]), __uint_as_float(s[c][x + 1]));
+#if FA_PACKED
+              v = __ffma2_rn(v, make_float2(p.scale_log2, p.scale_log2), make_float2(neg_m, neg_m));
+#else
+              v.x = fmaf(v.x, p.scale_log2, neg_m);
+              v.y = fmaf(v.y, p.scale_log2, neg_m);
+#endif
+              v.x = ex2_approx(v.x);
+              v.y = ex2_approx(v.y);
+#if FA_PACKED
+              lsum[c] = __fadd2_rn(lsum[c], v);
+#else
+              lsum[c].x += v.x;
+              lsum[c].y += v.y;
+#endif
+              s[c][x] = __float_as_uint(v.x);
+              s[c][x + 1] = __float_as_uint(v.y);
             }
-          tmem_st32(tS, pk[0]);
-          tmem_st32(tS + 32, pk[1]);
+          }
+        };
+        auto store_p = [&](int c0, int c1) {  // P columns 32*c0 .. 32*c1-1 -> TMEM (in place over S)
+          if constexpr (DT == DT_F32) {
+#pragma unroll
+            for (int c = c0; c < c1; ++c) tmem_st32(tS + c * 32, s[c]);
+          } else {
+#pragma unroll
+            for (int c = c0; c < c1; c += 2) {
+              uint32_t pk[32];
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int x = 0; x < 16; ++x) {
+                  const float a = __uint_as_float(s[c + cc][2 * x]), b = __uint_as_float(s[c + cc][2 * x + 1]);
+                  pk[cc * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+                }
+              tmem_st32(tS + (c / 2) * 32, pk);
+            }
+          }
+        };
+        if (FA_P_HALVES) {
+          exp_blocks(0, 2);
+          store_p(0, 2);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[2 * i]);
+          exp_blocks(2, 4);
+          store_p(2, 4);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[2 * i + 1]);
+        } else {
+          exp_blocks(0, 4);
+          store_p(0, 4);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[2 * i]);
         }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[i]);
+        l += ((lsum[0].x + lsum[0].y) + (lsum[1].x + lsum[1].y)) + ((lsum[2].x + lsum[2].y) + (lsum[3].x + lsum[3].y));
       }
 
       // ------------------------------- epilogue: O_i / l -------------------------------------

@@ -50,6 +50,20 @@ EncodeFn get_encode_fn() {
 
 int elem_size(int dtype) { return dtype == FA_DTYPE_F32 ? 4 : 2; }
 
+// SM count of the current device, queried once per device (not per call like the reference's
+// cudaGetDeviceProperties, flash_attention_v1.h:280-281).
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // [BH][L][D] row-major tensor, box = one 128-byte-wide, `box_rows`-row block of one head, 128B swizzle.
 // Rows past L are zero-filled on load and clipped on store, so tiles never leak into the next head.
 int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false) {
@@ -102,13 +116,20 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.BH = BH;
   p.kv_per_split = SPLIT ? kv_per_split : L;
   p.n_splits = SPLIT ? n_splits : 1;
+  p.n_qpairs = (L + 255) / 256;
+  const long long items = (long long)BH * p.n_splits * p.n_qpairs;
+  if (items > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, split, q-tile) work items");
+  p.n_items = int(items);
   p.scale = 1.0f / std::sqrt(float(D));
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = o_accum;
   p.lse_accum = lse_accum;
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-  dim3 grid((L + 255) / 256, BH, SPLIT ? n_splits : 1);
+  // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...
+  const int sms = sm_count();
+  if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
+  const int grid = p.n_items < sms ? p.n_items : sms;
   kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
@@ -146,6 +167,8 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   p.BH = BH;
   p.kv_per_split = L;
   p.n_splits = 1;
+  p.n_qpairs = 0;
+  p.n_items = 0;
   p.scale = 1.0f / std::sqrt(float(D));
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = nullptr;

@@ -10,17 +10,22 @@
 //   S = Q K^T / sqrt(d); m' = max(m, rowmax S); P = exp(S - m'); l = l*alpha + rowsum P; O = O*alpha + P V.
 //
 // B200 mapping
-//   CTA = one pair of 128-row Q tiles of one (b,h) head [x one KV split], 10 warps:
+//   PERSISTENT grid (one CTA per SM).  A work item = one pair of 128-row Q tiles of one (b,h) head [x one KV split];
+//   CTA c walks items c, c+gridDim.x, ... (q-pair index fastest, so neighbouring SMs stream the same head's K/V out
+//   of L2).  Barrier phases, the K/V ring and TMEM live across items, so the next item's Q/K/V loads and first QK^T
+//   overlap the previous item's epilogue instead of paying a launch-style prologue/epilogue per tile pair.
+//   12 warps:
 //     warps 0-3  softmax warpgroup for Q tile 0   (thread <-> S/O row: no shuffles for row max / row sum)
 //     warps 4-7  softmax warpgroup for Q tile 1
-//     warp  8    TMA producer (one lane): Q tiles once, then the K_j / V_j ring
-//     warp  9    tcgen05.mma issuer (one lane)      (warps 10-11 idle: setmaxnreg works per warpgroup)
+//     warp  8    TMA producer (one elected lane): Q tiles, then the K_j / V_j ring
+//     warp  9    tcgen05.mma issuer (one elected lane)      (warps 10-11 idle: setmaxnreg works per warpgroup)
 //   TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P overwrites S in place
 //     (packed 16-bit pairs for bf16/fp16, fp32 words for tf32) and feeds the PV MMA as the TMEM A operand.
-//   smem: Q 2 tiles + NS-stage K/V ring, all 128B-swizzled [128 rows x 128 B] blocks written by TMA.
-//   The two Q tiles ping-pong on the tensor pipe: while warpgroup i runs softmax on S_i the MMA warp
-//   issues PV/QK for tile 1-i.  O is rescaled lazily (only when the running max moves by > 2^8), by the
-//   softmax warpgroup itself, so there is no separate correction stage on the critical path.
+//   smem: Q 2 tiles + NS-stage K/V ring + one 16 KB output staging block per warpgroup, all 128B-swizzled
+//     [128 rows x 128 B] blocks moved by TMA.
+//   The two Q tiles ping-pong on the tensor pipe: while warpgroup i runs softmax on S_i the MMA warp issues PV/QK for
+//   tile 1-i.  P is published in two 64-key halves so PV starts while the second half is still being exponentiated.
+//   O is rescaled lazily (only when the running max moves by > 2^8) by the softmax warpgroup itself.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -36,6 +41,8 @@ struct FwdParams {
   int BH;            // B*H
   int kv_per_split;  // keys handled by one split (== L when SPLIT is false)
   int n_splits;
+  int n_qpairs;      // ceil(L / 256)
+  int n_items;       // BH * n_splits * n_qpairs
   float scale_log2;  // log2(e)/sqrt(d)
   float scale;       // 1/sqrt(d)
   float* o_accum;    // [n_splits][BH][L][D] fp32, each split normalised by its own l   (SPLIT only)
@@ -56,12 +63,12 @@ struct FwdTraits {
   static constexpr int BLK_BYTES = 128 * 128;      // 128 rows x 128 B
   static constexpr int TILE_BYTES = NBLK * BLK_BYTES;
   static constexpr int UK = 32 / ES;               // MMA K: 16 (16-bit) / 8 (tf32)
-  static constexpr int NS = (TILE_BYTES >= 32768) ? 5 : 8;  // K/V ring depth
+  static constexpr int NS = (TILE_BYTES >= 32768) ? 4 : 8;  // K/V ring depth
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S = 0, TM_O = 256;
   static_assert(256 + 2 * D <= 512, "S and O accumulators must fit TMEM");
-  static constexpr int NUM_BARS = 2 + 2 * NS + 2 + 4 + 2;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + NUM_BARS * 8 + 16;
+  static constexpr int NUM_BARS = 2 + 2 + 2 * NS + 2 + 4 + 2 + 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + 2 * BLK_BYTES + NUM_BARS * 8 + 16;
   static constexpr int THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle}
 };
 
@@ -73,15 +80,38 @@ struct FwdTraits {
 #define FA_PACKED 1     // 1: packed fp32x2 FFMA2 / FADD2 for the scale-subtract and the row sum (halves their issue slots)
 #endif
 
+#ifndef FA_PREISSUE
+#define FA_PREISSUE 0   // 1: issue the next item's first QK^T right behind this item's last PV (helps 1-tile items by ~3 %,
+#endif                  //    costs ~2 % at d=128 / L>=1024 on B200, so off)
+
 // Softmax rescale threshold in log2 units (P values stay <= 2^8; exact after the final O / l).
 constexpr float kRescaleThreshold = 8.0f;
+
+struct ItemCoord {
+  int q_row0, bh, split, kv_begin, kv_end, n_tiles, n_q;
+};
+
+template <bool SPLIT>
+__device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
+  ItemCoord c;
+  const int qp = item % p.n_qpairs;
+  const int rest = item / p.n_qpairs;
+  c.split = SPLIT ? rest % p.n_splits : 0;
+  c.bh = SPLIT ? rest / p.n_splits : rest;
+  c.q_row0 = qp * 256;
+  c.kv_begin = SPLIT ? c.split * p.kv_per_split : 0;
+  c.kv_end = SPLIT ? min(p.L, c.kv_begin + p.kv_per_split) : p.L;
+  c.n_tiles = (c.kv_end - c.kv_begin + 127) / 128;
+  c.n_q = (p.L - c.q_row0 > 128) ? 2 : 1;
+  return c;
+}
 
 template <int D, int DT, bool SPLIT>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
   using T = FwdTraits<D, DT>;
-  constexpr int ES = T::ES, BM = T::BM, BN = T::BN, NBLK = T::NBLK, BLK_ELEMS = T::BLK_ELEMS;
+  constexpr int BM = T::BM, BN = T::BN, NBLK = T::NBLK, BLK_ELEMS = T::BLK_ELEMS;
   constexpr int BLK_BYTES = T::BLK_BYTES, TILE_BYTES = T::TILE_BYTES, UK = T::UK, NS = T::NS;
   constexpr uint32_t KIND = T::KIND;
 
@@ -89,37 +119,34 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + 2 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NS * TILE_BYTES);
-  uint64_t* q_full = bars;              // [2]  TMA -> MMA
-  uint64_t* kv_full = q_full + 2;       // [NS] TMA -> MMA
-  uint64_t* kv_empty = kv_full + NS;    // [NS] MMA (tcgen05.commit) -> TMA
+  uint8_t* sOut = sKV + NS * TILE_BYTES;  // [2] one 128-row x 128-B staging block per softmax warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * BLK_BYTES);
+  uint64_t* q_full = bars;              // [2]  TMA -> MMA: Q_i of this item landed
+  uint64_t* q_empty = q_full + 2;       // [2]  MMA (commit) -> TMA: every QK_i of this item retired, Q_i may be overwritten
+  uint64_t* kv_full = q_empty + 2;      // [NS] TMA -> MMA
+  uint64_t* kv_empty = kv_full + NS;    // [NS] MMA (commit) -> TMA
   uint64_t* s_full = kv_empty + NS;     // [2]  MMA -> softmax: S_i(j) ready (and every earlier MMA retired)
-  uint64_t* p_full = s_full + 2;        // [2][2] softmax (128 arrivals) -> MMA: P_i(j) (key half h) in TMEM, O_i rescaled
-  uint64_t* o_done = p_full + 4;        // [2]  MMA -> softmax: last PV_i retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* p_full = s_full + 2;        // [2][2] softmax (128 arrivals) -> MMA: key-half h of P_i(j) in TMEM, O_i rescaled
+  uint64_t* o_done = p_full + 4;        // [2]  MMA -> softmax: last PV_i of this item retired
+  uint64_t* o_free = o_done + 2;        // [2]  softmax (128 arrivals) -> MMA: O_i read out, next item may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * (2 * BM);
-  const int bh = blockIdx.y;
-  const int split = SPLIT ? blockIdx.z : 0;
-  const int kv_begin = SPLIT ? split * p.kv_per_split : 0;
-  const int kv_end = SPLIT ? min(p.L, kv_begin + p.kv_per_split) : p.L;
-  const int n_tiles = (kv_end - kv_begin + BN - 1) / BN;
-  const int n_q = (p.L - q_row0 > BM) ? 2 : 1;
 
   if (warp == 9 && lane == 0) {
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[2 * i], 128);
       mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
+      mbar_init(&o_free[i], 128);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
     }
     fence_mbar_init();
   }
@@ -138,121 +165,177 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Register re-split (launch gives every thread 168): the data-movement warpgroup keeps 40, each softmax
-  // thread gets 232 so a full 128-column S row plus its packed P stays in registers.  setmaxnreg sits at the top
-  // of each role branch (no control-flow merge after it) so ptxas allocates each role under its own budget.
+  // Register re-split (launch gives every thread 168): the data-movement warpgroup keeps 72, each softmax thread gets
+  // 216 (2*128*216 + 128*72 = 384*168 exactly: an inc that cannot be met from the launch allocation blocks forever).  setmaxnreg sits at the top of each role branch (no control-flow merge after it) so ptxas allocates each
+  // role under its own budget.
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 8) {
-    // ===================================== TMA producer =====================================
-    if (elect_one_sync()) {
-      auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int row) {
-        mbar_arrive_expect_tx(bar, TILE_BYTES);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 8) {
+      // ===================================== TMA producer =====================================
+      if (elect_one_sync()) {
+        int tt = 0;            // K/V tiles issued so far (ring position), across items
+        int nq0 = 0, nq1 = 0;  // Q_i loads issued so far
+        auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int row, int bh) {
+          mbar_arrive_expect_tx(bar, TILE_BYTES);
 #pragma unroll
-        for (int b = 0; b < NBLK; ++b) tma_load_3d(dst + b * BLK_BYTES, map, bar, b * BLK_ELEMS, row, bh);
-      };
-      auto load_kv = [&](int t) {  // t = 2j -> K_j, t = 2j+1 -> V_j
-        const int stage = t % NS;
-        if (t >= NS) mbar_wait(&kv_empty[stage], ((t / NS) - 1) & 1);
-        load_tile(sKV + stage * TILE_BYTES, (t & 1) ? &tmV : &tmK, &kv_full[stage], kv_begin + (t >> 1) * BN);
-      };
-      load_tile(sQ, &tmQ, &q_full[0], q_row0);
-      load_kv(0);
-      if (n_q > 1) load_tile(sQ + TILE_BYTES, &tmQ, &q_full[1], q_row0 + BM);
-      for (int t = 1; t < 2 * n_tiles; ++t) load_kv(t);
-    }
-  } else if (warp == 9) {
-    // ===================================== MMA issuer ========================================
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, D, 0, 1);
-      constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);         // K-major, 8-row atoms 1024 B apart
-      // MN-major V: LBO = next 128-B column block; 8-key atoms 1024 B apart.  32-bit (tf32) MN-major operands only
-      // exist in the 128B-swizzle / 32B-atom layout (4-key atoms, 512 B apart) — V's tensor map matches (fa_api.cu).
-      constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
-                                              : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
-      const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
-
-      auto qk = [&](int i, int stage) {  // S_i = Q_i K^T
-        const uint32_t a_base = sQ_addr + i * TILE_BYTES, b_base = sKV_addr + stage * TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < D / UK; ++k) {
-          const uint32_t off = (k / 4) * BLK_BYTES + (k % 4) * 32;
-          umma_ss<KIND>(tmem_base + T::TM_S + i * BN, make_smem_desc(a_base + off, hiK),
-                        make_smem_desc(b_base + off, hiK), idesc_qk, k > 0 ? 1u : 0u);
+          for (int b = 0; b < NBLK; ++b) tma_load_3d(dst + b * BLK_BYTES, map, bar, b * BLK_ELEMS, row, bh);
+        };
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const ItemCoord c = decode_item<SPLIT>(item, p);
+          auto load_q = [&](int i, int& n) {
+            if (n > 0) mbar_wait(&q_empty[i], (n - 1) & 1);
+            load_tile(sQ + i * TILE_BYTES, &tmQ, &q_full[i], c.q_row0 + i * BM, c.bh);
+            ++n;
+          };
+          auto load_kv = [&](int t) {  // t = 2j -> K_j, t = 2j+1 -> V_j
+            const int stage = tt % NS;
+            if (tt >= NS) mbar_wait(&kv_empty[stage], ((tt / NS) - 1) & 1);
+            load_tile(sKV + stage * TILE_BYTES, (t & 1) ? &tmV : &tmK, &kv_full[stage], c.kv_begin + (t >> 1) * BN, c.bh);
+            ++tt;
+          };
+          load_q(0, nq0);
+          load_kv(0);
+          if (c.n_q > 1) load_q(1, nq1);
+          for (int t = 1; t < 2 * c.n_tiles; ++t) load_kv(t);
         }
-      };
-      auto pv = [&](int i, int stage, uint32_t acc, int kk0, int kk1) {  // O_i (+)= P_i V  (K-steps kk0..kk1-1)
-        const uint32_t b_base = sKV_addr + stage * TILE_BYTES;
-#pragma unroll
-        for (int kk = kk0; kk < kk1; ++kk) {
-          umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_S + i * BN + kk * 8,
-                        make_smem_desc(b_base + kk * UK * 128, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
-        }
-      };
-
-      mbar_wait(&kv_full[0], 0);
-      for (int i = 0; i < n_q; ++i) {
-        mbar_wait(&q_full[i], 0);
-        tc_fence_after();
-        qk(i, 0);
-        tc_commit(&s_full[i]);
       }
-      tc_commit(&kv_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int tv = 2 * j + 1, tk = 2 * j + 2;
-        const bool has_next = (j + 1 < n_tiles);
-        mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
-        for (int i = 0; i < n_q; ++i) {
-          constexpr int KT = BN / UK;
-          mbar_wait(&p_full[2 * i], j & 1);
-          tc_fence_after();
-          if (FA_P_HALVES) {
-            pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
-            mbar_wait(&p_full[2 * i + 1], j & 1);
+    } else if (warp == 9) {
+      // ===================================== MMA issuer ========================================
+      if (elect_one_sync()) {
+        constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, D, 0, 1);
+        constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);  // K-major, 8-row atoms 1024 B apart
+        // MN-major V: LBO = next 128-B column block; 8-key atoms 1024 B apart.  32-bit (tf32) MN-major operands only
+        // exist in the 128B-swizzle / 32B-atom layout (4-key atoms, 512 B apart) — V's tensor map matches (fa_api.cu).
+        constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
+                                                : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
+        constexpr int KT = BN / UK;
+        const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+
+        auto qk = [&](int i, int stage) {  // S_i = Q_i K^T
+          const uint32_t a_base = sQ_addr + i * TILE_BYTES, b_base = sKV_addr + stage * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < D / UK; ++k) {
+            const uint32_t off = (k / 4) * BLK_BYTES + (k % 4) * 32;
+            umma_ss<KIND>(tmem_base + T::TM_S + i * BN, make_smem_desc(a_base + off, hiK),
+                          make_smem_desc(b_base + off, hiK), idesc_qk, k > 0 ? 1u : 0u);
+          }
+        };
+        auto pv = [&](int i, int stage, uint32_t acc, int kk0, int kk1) {  // O_i (+)= P_i V  (K-steps kk0..kk1-1)
+          const uint32_t b_base = sKV_addr + stage * TILE_BYTES;
+#pragma unroll
+          for (int kk = kk0; kk < kk1; ++kk) {
+            umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_S + i * BN + kk * 8,
+                          make_smem_desc(b_base + kk * UK * 128, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
+          }
+        };
+
+        int tt = 0;            // K/V tiles consumed so far (ring position), across items
+        int nt[2] = {0, 0};    // KV tiles processed for Q tile i (phase of s_full / p_full), across items
+        int ni[2] = {0, 0};    // items processed for Q tile i (phase of q_full / o_done / o_free)
+        bool pre[2] = {false, false};  // QK_i(0) of the coming item was already issued behind the previous item's last PV_i
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const ItemCoord c = decode_item<SPLIT>(item, p);
+          const int t0 = tt;   // ring index of K_0 of this item
+          const int item_n = item + gridDim.x;
+          const bool has_item_n = item_n < p.n_items;
+          ItemCoord cn = c;
+          if (has_item_n) cn = decode_item<SPLIT>(item_n, p);
+          const int tn0 = t0 + 2 * c.n_tiles;  // ring index of the next item's K_0
+
+          // first QK^T of a Q tile: S_i = Q_i K_0^T (for the tiles not pre-issued at the end of the previous item)
+          auto first_qk = [&](int i, int ring_idx, int q_phase, int n_tiles_of_item) {
+            mbar_wait(&kv_full[ring_idx % NS], (ring_idx / NS) & 1);
+            mbar_wait(&q_full[i], q_phase & 1);
             tc_fence_after();
-            pv(i, tv % NS, 1u, KT / 2, KT);
-          } else {
-            pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
-          }
-          if (!has_next) tc_commit(&o_done[i]);
-          if (has_next) {
-            if (i == 0) {
-              mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
-              tc_fence_after();
-            }
-            qk(i, tk % NS);
+            qk(i, ring_idx % NS);
             tc_commit(&s_full[i]);
+            if (n_tiles_of_item == 1) tc_commit(&q_empty[i]);
+          };
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {  // compile-time i: the per-tile counters stay in registers
+            if (i >= c.n_q || pre[i]) continue;
+            first_qk(i, t0, ni[i], c.n_tiles);
           }
+          tc_commit(&kv_empty[t0 % NS]);  // K_0: both QK(0) are issued by now
+          for (int j = 0; j < c.n_tiles; ++j) {
+            const int tv = t0 + 2 * j + 1, tk = t0 + 2 * j + 2;
+            const bool has_next = (j + 1 < c.n_tiles);
+            mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i >= c.n_q) continue;
+              if (j == 0 && ni[i] > 0) {
+                // PV_i(0) overwrites O_i: the previous item's epilogue must have read it out of TMEM
+                mbar_wait(&o_free[i], (ni[i] - 1) & 1);
+              }
+              mbar_wait(&p_full[2 * i], nt[i] & 1);
+              tc_fence_after();
+              if (FA_P_HALVES) {
+                pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+                mbar_wait(&p_full[2 * i + 1], nt[i] & 1);
+                tc_fence_after();
+                pv(i, tv % NS, 1u, KT / 2, KT);
+              } else {
+                pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
+              }
+              ++nt[i];
+              if (has_next) {
+                if (i == 0) {
+                  mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
+                  tc_fence_after();
+                }
+                qk(i, tk % NS);
+                tc_commit(&s_full[i]);
+                if (j + 2 == c.n_tiles) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
+              } else {
+                tc_commit(&o_done[i]);
+                // Keep the tile stream going across the item boundary: the next item's S_i = Q_i' K_0'^T follows
+                // this item's last PV_i exactly like QK_i(j+1) follows PV_i(j) inside an item.
+                pre[i] = FA_PREISSUE && has_item_n && i < cn.n_q;
+                if (pre[i]) first_qk(i, tn0, ni[i] + 1, cn.n_tiles);
+              }
+            }
+            tc_commit(&kv_empty[tv % NS]);
+            if (has_next) tc_commit(&kv_empty[tk % NS]);
+          }
+          if (c.n_q < 2) pre[1] = false;
+          tt = tn0;
+          ++ni[0];
+          if (c.n_q > 1) ++ni[1];
         }
-        tc_commit(&kv_empty[tv % NS]);
-        if (has_next) tc_commit(&kv_empty[tk % NS]);
       }
     }
-  }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ===================================== softmax warpgroups =================================
     const int i = warp >> 2;  // which Q tile
-    if (i < n_q) {
-      const int row = (warp & 3) * 32 + lane;
-      const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-      const uint32_t tS = t_lane + T::TM_S + i * BN;
-      const uint32_t tO = t_lane + T::TM_O + i * D;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t tS = t_lane + T::TM_S + i * BN;
+    const uint32_t tO = t_lane + T::TM_O + i * D;
+    uint8_t* sO = sOut + i * BLK_BYTES;
+    const bool storer = ((warp & 3) == 0) && (lane == 0);
+    int nt = 0;  // KV tiles processed (phase of s_full / p_full), across items
+    int ni = 0;  // items processed (phase of o_done)
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item<SPLIT>(item, p);
+      if (i >= c.n_q) continue;  // this item has a single Q tile
       float m_used = -CUDART_INF_F;
       float l = 0.f;
 
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&s_full[i], j & 1);
+      for (int j = 0; j < c.n_tiles; ++j, ++nt) {
+        mbar_wait(&s_full[i], nt & 1);
         tc_fence_after();
         uint32_t s[4][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+        for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s[cc]);
         tc_wait_ld();
 
         // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
         // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
-        const int valid = kv_end - (kv_begin + j * BN);
+        const int valid = c.kv_end - (c.kv_begin + j * BN);
         float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
         if (valid >= BN) {
 #pragma unroll
@@ -264,10 +347,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
             for (int x = 0; x < 32; ++x)
-              if (c * 32 + x >= valid) s[c][x] = __float_as_uint(-CUDART_INF_F);
+              if (cc * 32 + x >= valid) s[cc][x] = __float_as_uint(-CUDART_INF_F);
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
             mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
@@ -290,13 +373,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (need) m_used = mx;
             l *= alpha;
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
+            for (int cc = 0; cc < D / 32; ++cc) {
               uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
+              tmem_ld32(tO + cc * 32, o);
               tc_wait_ld();
 #pragma unroll
               for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-              tmem_st32(tO + c * 32, o);
+              tmem_st32(tO + cc * 32, o);
             }
           }
         }
@@ -308,8 +391,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int x = 0; x < 32; x += 2) {
 #pragma unroll
-            for (int c = c0; c < c1; ++c) {
-              float2 v = make_float2(__uint_as_float(s[c][x]), __uint_as_float(s[c][x + 1]));
+            for (int cc = c0; cc < c1; ++cc) {
+              float2 v = make_float2(__uint_as_float(s[cc][x]), __uint_as_float(s[cc][x + 1]));
 #if FA_PACKED
               v = __ffma2_rn(v, make_float2(p.scale_log2, p.scale_log2), make_float2(neg_m, neg_m));
 #else
@@ -319,32 +402,32 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               v.x = ex2_approx(v.x);
               v.y = ex2_approx(v.y);
 #if FA_PACKED
-              lsum[c] = __fadd2_rn(lsum[c], v);
+              lsum[cc] = __fadd2_rn(lsum[cc], v);
 #else
-              lsum[c].x += v.x;
-              lsum[c].y += v.y;
+              lsum[cc].x += v.x;
+              lsum[cc].y += v.y;
 #endif
-              s[c][x] = __float_as_uint(v.x);
-              s[c][x + 1] = __float_as_uint(v.y);
+              s[cc][x] = __float_as_uint(v.x);
+              s[cc][x + 1] = __float_as_uint(v.y);
             }
           }
         };
         auto store_p = [&](int c0, int c1) {  // P columns 32*c0 .. 32*c1-1 -> TMEM (in place over S)
           if constexpr (DT == DT_F32) {
 #pragma unroll
-            for (int c = c0; c < c1; ++c) tmem_st32(tS + c * 32, s[c]);
+            for (int cc = c0; cc < c1; ++cc) tmem_st32(tS + cc * 32, s[cc]);
           } else {
 #pragma unroll
-            for (int c = c0; c < c1; c += 2) {
+            for (int cc = c0; cc < c1; cc += 2) {
               uint32_t pk[32];
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc)
+              for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int x = 0; x < 16; ++x) {
-                  const float a = __uint_as_float(s[c + cc][2 * x]), b = __uint_as_float(s[c + cc][2 * x + 1]);
-                  pk[cc * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+                  const float a = __uint_as_float(s[cc + h][2 * x]), b = __uint_as_float(s[cc + h][2 * x + 1]);
+                  pk[h * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
                 }
-              tmem_st32(tS + (c / 2) * 32, pk);
+              tmem_st32(tS + (cc / 2) * 32, pk);
             }
           }
         };
@@ -370,72 +453,70 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
 
       // ------------------------------- epilogue: O_i / l -------------------------------------
-      mbar_wait(&o_done[i], 0);
+      mbar_wait(&o_done[i], ni & 1);
+      ++ni;
       tc_fence_after();
+      uint32_t o[D / 32][32];
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) tmem_ld32(tO + cc * 32, o[cc]);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&o_free[i]);  // O_i is in registers: the MMA warp may start the next item's PV_i
       const float inv_l = 1.0f / l;
-      const int row_g = q_row0 + i * BM + row;
+      const int row_g = c.q_row0 + i * BM + row;
       if constexpr (SPLIT) {
         if (row_g < p.L) {
-          const size_t ridx = (size_t(split) * p.BH + bh) * p.L + row_g;
+          const size_t ridx = (size_t(c.split) * p.BH + c.bh) * p.L + row_g;
           p.lse_accum[ridx] = m_used * p.scale + __logf(l);
-        }
-        float* dst = p.o_accum + ((size_t(split) * p.BH + bh) * p.L + row_g) * D;
+          float* dst = p.o_accum + ridx * D;
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tc_wait_ld();
-          if (row_g < p.L) {
+          for (int cc = 0; cc < D / 32; ++cc)
 #pragma unroll
             for (int x = 0; x < 32; x += 4) {
-              float4 v = make_float4(__uint_as_float(o[x]) * inv_l, __uint_as_float(o[x + 1]) * inv_l,
-                                     __uint_as_float(o[x + 2]) * inv_l, __uint_as_float(o[x + 3]) * inv_l);
-              *reinterpret_cast<float4*>(dst + c * 32 + x) = v;
+              float4 v = make_float4(__uint_as_float(o[cc][x]) * inv_l, __uint_as_float(o[cc][x + 1]) * inv_l,
+                                     __uint_as_float(o[cc][x + 2]) * inv_l, __uint_as_float(o[cc][x + 3]) * inv_l);
+              *reinterpret_cast<float4*>(dst + cc * 32 + x) = v;
             }
-          }
         }
       } else {
-        // Stage the tile in Q_i's (now dead) smem buffer in the same 128B-swizzled block layout, then TMA-store it.
-        uint8_t* sO = sQ + i * TILE_BYTES;
+        // One 128-byte column block at a time through this warpgroup's staging block (same 128B swizzle), TMA store.
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tc_wait_ld();
-          constexpr int CH = 32 * ES / 16;  // 16-byte chunks per 32 columns
+        for (int b = 0; b < NBLK; ++b) {
+          if (storer) tma_store_wait_read_all();  // the previous store has finished reading the staging block
+          named_bar_sync(1 + i, 128);
 #pragma unroll
-          for (int u = 0; u < CH; ++u) {
+          for (int u = 0; u < 8; ++u) {           // 8 x 16-byte chunks per 128-byte row
             uint4 v;
             if constexpr (DT == DT_F32) {
-              v.x = __float_as_uint(__uint_as_float(o[4 * u + 0]) * inv_l);
-              v.y = __float_as_uint(__uint_as_float(o[4 * u + 1]) * inv_l);
-              v.z = __float_as_uint(__uint_as_float(o[4 * u + 2]) * inv_l);
-              v.w = __float_as_uint(__uint_as_float(o[4 * u + 3]) * inv_l);
+              const int e = b * BLK_ELEMS + u * 4;  // output column of the first element of this chunk
+              v.x = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 0]) * inv_l);
+              v.y = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 1]) * inv_l);
+              v.z = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 2]) * inv_l);
+              v.w = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 3]) * inv_l);
             } else {
-              auto pk2 = [&](int e) {
-                const float a = __uint_as_float(o[e]) * inv_l, b = __uint_as_float(o[e + 1]) * inv_l;
-                return (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+              const int e = b * BLK_ELEMS + u * 8;
+              auto pk2 = [&](int ee) {
+                const float a0 = __uint_as_float(o[ee / 32][ee % 32]) * inv_l;
+                const float a1 = __uint_as_float(o[ee / 32][ee % 32 + 1]) * inv_l;
+                return (DT == DT_BF16) ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
               };
-              v.x = pk2(8 * u + 0);
-              v.y = pk2(8 * u + 2);
-              v.z = pk2(8 * u + 4);
-              v.w = pk2(8 * u + 6);
+              v.x = pk2(e + 0);
+              v.y = pk2(e + 2);
+              v.z = pk2(e + 4);
+              v.w = pk2(e + 6);
             }
-            const int q = c * CH + u;  // 16-byte chunk index within the row
-            uint8_t* dst = sO + (q >> 3) * BLK_BYTES + row * 128 + (((q & 7) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = v;
+            *reinterpret_cast<uint4*>(sO + row * 128 + ((u ^ (row & 7)) << 4)) = v;
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + i, 128);
-        if ((warp & 3) == 0 && lane == 0) {
-#pragma unroll
-          for (int b = 0; b < NBLK; ++b) tma_store_3d(&tmO, sO + b * BLK_BYTES, b * BLK_ELEMS, q_row0 + i * BM, bh);
-          tma_store_commit();
-          tma_store_wait_all();
+          fence_proxy_async_smem();
+          named_bar_sync(1 + i, 128);
+          if (storer) {
+            tma_store_3d(&tmO, sO, b * BLK_ELEMS, c.q_row0 + i * BM, c.bh);
+            tma_store_commit();
+          }
         }
       }
     }
+    if (!SPLIT && storer) tma_store_wait_read_all();  // smem must outlive the last store's read
   }
 
   tc_fence_before();

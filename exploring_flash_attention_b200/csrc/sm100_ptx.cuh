@@ -141,6 +141,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// waits only until the committed stores have finished READING shared memory (the staging buffer may be reused)
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit

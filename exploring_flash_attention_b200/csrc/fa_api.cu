@@ -75,11 +75,13 @@ int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, i
                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t dims[3] = {cuuint64_t(D), cuuint64_t(L), cuuint64_t(BH)};
   cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(L) * D * es};
-  cuuint32_t box[3] = {cuuint32_t(128 / es), cuuint32_t(box_rows), 1};
+  const int swb = (D * es >= 128) ? 128 : 64;  // swizzle span = bytes of one block row (64 only for 16-bit d = 32)
+  cuuint32_t box[3] = {cuuint32_t(swb / es), cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   // 32-bit MN-major UMMA operands (fp32 V) must use the 32B-atom flavour of the 128B swizzle.
-  const CUtensorMapSwizzle swz =
-      (mn_major_operand && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle swz = (swb == 64)                      ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : (mn_major_operand && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                                 : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
@@ -145,11 +147,13 @@ int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, i
   FA_CASE(64, fa::DT_BF16)
   FA_CASE(128, fa::DT_F16)
   FA_CASE(64, fa::DT_F16)
+  FA_CASE(32, fa::DT_BF16)
+  FA_CASE(32, fa::DT_F16)
   FA_CASE(32, fa::DT_F32)
   FA_CASE(64, fa::DT_F32)
 #undef FA_CASE
   return fail(FA_ERR_UNSUPPORTED_D,
-              "fused-tile kernel serves d in {64,128} for bf16/fp16 and d in {32,64} for fp32; got d=" +
+              "fused-tile kernel serves d in {32,64,128} for bf16/fp16 and d in {32,64} for fp32; got d=" +
                   std::to_string(d) + " dtype=" + std::to_string(dtype));
 }
 

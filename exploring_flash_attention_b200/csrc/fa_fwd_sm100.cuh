@@ -21,8 +21,8 @@
 //     warp  9    tcgen05.mma issuer (one elected lane)      (warps 10-11 idle: setmaxnreg works per warpgroup)
 //   TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P overwrites S in place
 //     (packed 16-bit pairs for bf16/fp16, fp32 words for tf32) and feeds the PV MMA as the TMEM A operand.
-//   smem: Q 2 tiles + NS-stage K/V ring + one 16 KB output staging block per warpgroup, all 128B-swizzled
-//     [128 rows x 128 B] blocks moved by TMA.
+//   smem: Q 2 tiles + NS-stage K/V ring + one output staging block per warpgroup, all swizzled [128 rows x 128 B]
+//     blocks moved by TMA (64-byte rows / 64B swizzle when the head-dim row is only 64 bytes: 16-bit d = 32).
 //   The two Q tiles ping-pong on the tensor pipe: while warpgroup i runs softmax on S_i the MMA warp issues PV/QK for
 //   tile 1-i.  P is published in two 64-key halves so PV starts while the second half is still being exponentiated.
 //   O is rescaled lazily (only when the running max moves by > 2^8) by the softmax warpgroup itself.
@@ -57,10 +57,13 @@ struct FwdTraits {
   static constexpr int BM = 128;                   // query rows per tile (= TMEM lanes)
   static constexpr int BN = 128;                   // keys per KV tile
   static constexpr int ROW_BYTES = D * ES;
-  static_assert(ROW_BYTES % 128 == 0, "head-dim row must be a whole number of 128-byte swizzle rows");
-  static constexpr int NBLK = ROW_BYTES / 128;     // 128-byte column blocks per tile
-  static constexpr int BLK_ELEMS = 128 / ES;       // elements per block row
-  static constexpr int BLK_BYTES = 128 * 128;      // 128 rows x 128 B
+  static constexpr int SWB = ROW_BYTES >= 128 ? 128 : 64;   // swizzle span = smem row pitch of a block (bytes)
+  static_assert(ROW_BYTES % SWB == 0 && ROW_BYTES >= 64, "head-dim row must be a whole number of swizzle rows");
+  static constexpr uint32_t SWZ = (SWB == 128) ? SWZ_128B : SWZ_64B;
+  static constexpr int NBLK = ROW_BYTES / SWB;     // column blocks per tile
+  static constexpr int BLK_ELEMS = SWB / ES;       // elements per block row
+  static constexpr int BLK_BYTES = 128 * SWB;      // 128 rows x SWB bytes
+  static constexpr int KPR = SWB / 32;             // MMA K-steps per block row
   static constexpr int TILE_BYTES = NBLK * BLK_BYTES;
   static constexpr int UK = 32 / ES;               // MMA K: 16 (16-bit) / 8 (tf32)
   static constexpr int NS = (TILE_BYTES >= 32768) ? 4 : 8;  // K/V ring depth
@@ -204,11 +207,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (elect_one_sync()) {
         constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, D, 0, 1);
-        constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);  // K-major, 8-row atoms 1024 B apart
+        constexpr uint64_t hiK = make_smem_desc_hi(16, 8 * T::SWB, T::SWZ);  // K-major, 8-row swizzle atoms
         // MN-major V: LBO = next 128-B column block; 8-key atoms 1024 B apart.  32-bit (tf32) MN-major operands only
         // exist in the 128B-swizzle / 32B-atom layout (4-key atoms, 512 B apart) — V's tensor map matches (fa_api.cu).
         constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
-                                                : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
+                                                : make_smem_desc_hi(BLK_BYTES, 8 * T::SWB, T::SWZ);
         constexpr int KT = BN / UK;
         const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
 
@@ -216,7 +219,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const uint32_t a_base = sQ_addr + i * TILE_BYTES, b_base = sKV_addr + stage * TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < D / UK; ++k) {
-            const uint32_t off = (k / 4) * BLK_BYTES + (k % 4) * 32;
+            const uint32_t off = (k / T::KPR) * BLK_BYTES + (k % T::KPR) * 32;
             umma_ss<KIND>(tmem_base + T::TM_S + i * BN, make_smem_desc(a_base + off, hiK),
                           make_smem_desc(b_base + off, hiK), idesc_qk, k > 0 ? 1u : 0u);
           }
@@ -226,7 +229,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
             umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_S + i * BN + kk * 8,
-                          make_smem_desc(b_base + kk * UK * 128, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
+                          make_smem_desc(b_base + kk * UK * T::SWB, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
           }
         };
 
@@ -485,7 +488,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (storer) tma_store_wait_read_all();  // the previous store has finished reading the staging block
           named_bar_sync(1 + i, 128);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {           // 8 x 16-byte chunks per 128-byte row
+          for (int u = 0; u < T::SWB / 16; ++u) {  // 16-byte chunks of one block row
             uint4 v;
             if constexpr (DT == DT_F32) {
               const int e = b * BLK_ELEMS + u * 4;  // output column of the first element of this chunk
@@ -505,7 +508,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               v.z = pk2(e + 4);
               v.w = pk2(e + 6);
             }
-            *reinterpret_cast<uint4*>(sO + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+            // 128B swizzle: chunk ^= row % 8; 64B swizzle: chunk ^= (row / 2) % 4   (address bits [4,7) ^ [7,10))
+            const int sw = (T::SWB == 128) ? (row & 7) : ((row >> 1) & 3);
+            *reinterpret_cast<uint4*>(sO + row * T::SWB + ((u ^ sw) << 4)) = v;
           }
           fence_proxy_async_smem();
           named_bar_sync(1 + i, 128);

@@ -220,6 +220,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 //   [32,46) stride-dim byte offset >> 4   [46,48) version (1 on sm_100)
 //   [49,52) base offset (0: tiles are 1024-B aligned)   [61,64) swizzle: 0 none, 1 = 128B/32B-atom, 2 = 128B, 4 = 64B, 6 = 32B
 constexpr uint32_t SWZ_128B = 2;
+constexpr uint32_t SWZ_64B = 4;
 constexpr uint32_t SWZ_128B_BASE32B = 1;  // 128B span swizzled in 32B chunks: the only MN-major layout for 32-bit operands
 
 __host__ __device__ constexpr uint64_t make_smem_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {

@@ -53,6 +53,18 @@ def standard_attention_cpu(Q, K, V, dtype_name=None, n_threads=0, head_begin=0, 
     return O
 
 
+def driver_inputs(B, H, L, d, dtype=np.float16, seed=42):
+    """Q, K, V exactly as the reference drivers synthesise them (srand(42), U[-1,1], Q->K->V, rounded to `dtype`)."""
+    lib = _load(HERE / "liboracle.so")
+    fn = lib.oracle_driver_uniform
+    fn.restype = None
+    fn.argtypes = [ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+    n = B * H * L * d
+    buf = np.empty(3 * n, dtype=np.float32)
+    fn(seed, 0, 3 * n, buf.ctypes.data)
+    return tuple(buf[k * n:(k + 1) * n].reshape(B, H, L, d).astype(dtype) for k in range(3))
+
+
 def have_ref() -> bool:
     return (HERE / "_ref" / "libref_standard_f16.so").exists()
 

@@ -146,6 +146,15 @@ int oracle_standard_attention_cpu(const void* Q, const void* K, const void* V, v
   return failed ? -1 : 0;
 }
 
+/* The reference drivers' input synthesis: srand(seed) once, then ((float)rand() / RAND_MAX) * 2.0f - 1.0f per element,
+ * Q then K then V (flash_attention_v1/CUDA/driver.cu:71-75, :137, :168-170).  glibc's rand() stream is reproduced by
+ * calling glibc itself; `skip` values are drawn and discarded first (to reach K or V without materialising Q). */
+void oracle_driver_uniform(unsigned seed, size_t skip, size_t n, float* out) {
+  srand(seed);
+  for (size_t i = 0; i < skip; ++i) (void)rand();
+  for (size_t i = 0; i < n; ++i) out[i] = ((float)rand() / (float)RAND_MAX) * 2.0f - 1.0f;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -29,6 +29,8 @@ CASES = [
     ("v2_bf16_d64_C3", "v2", 4, 8, 256, 64, "bf16", 64),
     ("v2_bf16_d128", "v2", 1, 4, 1024, 128, "bf16", 256),
     ("v2_f32_d32_ragged", "v2", 1, 2, 500, 32, "f32", 96),
+    ("v1_f16_d32", "v1", 2, 2, 512, 32, "f16", 0),
+    ("C1_f16_full", "v1", 32, 8, 1024, 32, "f16", 0),
     ("C2_full", "v1", 32, 8, 1024, 128, "bf16", 0),
     ("C1_full", "v1", 32, 8, 1024, 32, "f32", 0),
     ("C3_full", "v2", 32, 8, 256, 64, "bf16", 64),

@@ -116,3 +116,12 @@ def test_c_restatement_storage_types_and_head_range():
     assert np.abs(Ob - refb).max() < 2e-3
     part = cpu.standard_attention_cpu(Q, K, V, head_begin=1, head_end=2)
     assert np.array_equal(part[0, 1], O32[0, 1]) and not part[0, 0].any() and not part[0, 2].any()
+
+
+@pytest.mark.parametrize("d,known", [(32, [-0.00755692, 0.00990295, -0.0185699]), (128, [0.020874, -0.0102615, 0.00642014])])
+def test_driver_inputs_and_cpu_reference_known_answers(d, known):
+    """the reference's CPU output O[0..2] for its drivers' own data (srand(42), U[-1,1], fp16,
+    B32 H8 L1024; flash_attention_v1/CUDA/driver.cu:137-177 and the tiled-d driver with d=128)."""
+    Q, K, V = cpu.driver_inputs(32, 8, 1024, d)
+    O = cpu.standard_attention_cpu(Q, K, V, head_begin=0, head_end=1)
+    np.testing.assert_allclose(O[0, 0, 0, :3].astype(np.float64), known, rtol=0, atol=6e-8)

@@ -53,6 +53,8 @@ CASES = [  # B, H, L, d, dtype
     (1, 3, 333, 128, torch.bfloat16), (1, 2, 100, 128, torch.bfloat16), (1, 2, 129, 64, torch.bfloat16),
     (1, 2, 1, 128, torch.bfloat16), (1, 2, 777, 32, torch.float32), (1, 1, 257, 64, torch.float32),
     (3, 1, 8, 64, torch.float16),
+    # 16-bit d = 32: 64-byte rows, 64B-swizzle instantiation (the reference V1 driver's own config is fp16 d=32)
+    (2, 2, 512, 32, torch.float16), (1, 3, 333, 32, torch.bfloat16), (1, 1, 100, 32, torch.float16),
 ]
 
 
@@ -113,6 +115,7 @@ def test_c5_full_size_sampled(ops):
     (4, 8, 256, 64, torch.bfloat16, 64),       # C3 geometry: 4 splits of 64 keys
     (1, 4, 1024, 128, torch.bfloat16, 256), (1, 2, 500, 32, torch.float32, 96), (1, 2, 300, 64, torch.float16, 300),
     (1, 2, 200, 128, torch.bfloat16, 8),       # 25 splits of 8 keys (one reference tile each)
+    (2, 2, 384, 32, torch.float16, 64),
 ])
 def test_v2_splitkv_and_combine_match_oracle(ops, B, H, L, d, dtype, kvs):
     Q, K, V = uniform_qkv(B, H, L, d, dtype)
@@ -275,3 +278,24 @@ def test_error_behaviour_on_device(ops):
     Q, K, V = uniform_qkv(1, 1, 64, 64, torch.bfloat16)
     with pytest.raises(FlashAttentionError):
         ops.flash_attention_v1(Q, K[:, :, :32], V)
+
+
+@pytest.mark.parametrize("which", ["v1", "tiled_d", "v2"])
+def test_reference_driver_mirrors_pass(ops, which, capsys):
+    """The three reference drivers' flows (full B32 H8 L1024 shapes on the GPU; CPU reference bounded to 8 heads)."""
+    from tests.drivers import driver
+    if which == "v1":
+        pytest.skip("fp16 d=32 needs the 64-byte-swizzle instantiation") if not _fp16_d32_supported(ops) else None
+    rc = driver.main([which, "--heads", "8"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "Test PASSED" in out, out[-800:]
+
+
+def _fp16_d32_supported(ops):
+    from exploring_flash_attention_b200 import FlashAttentionError
+    try:
+        Q, K, V = uniform_qkv(1, 1, 128, 32, torch.float16)
+        ops.flash_attention_v1(Q, K, V, sync=True)
+        return True
+    except FlashAttentionError:
+        return False

@@ -193,7 +193,9 @@ def run_ours(args):
         clock_note = "timed region shorter than the NVML polling period; sampled during an untimed replay of the same step"
 
     # ---- roofline of the dominant kernel (the one fused forward kernel per step), timed live on its stream
-    per_launch_ms = time_steps(step, args.steps, torch) / args.steps
+    # one kernel launch per step, launches back to back on one stream: the kernel's average duration over the timed
+    # region IS ms_step (a second timing pass after the clock-sampling replay would run power-capped and read lower)
+    per_launch_ms = ms_step
     achieved = flops(B, H, L, d) / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0),
                 "unit": "TFLOP/s", "frac": round(achieved / (pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0)), 4),
@@ -246,7 +248,7 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/)
-NCU_TRAFFIC_BYTES: dict = {}
+NCU_TRAFFIC_BYTES: dict = {"c2": 243_684_096}   # profiles/r1_fwd_c2_persistent_full.txt: 201.45 MB read + 42.24 MB written
 
 
 def side_measurements(torch, ops, pk):
@@ -299,13 +301,14 @@ def side_measurements(torch, ops, pk):
         ms_all = timed(lambda: ops.flash_attention_v2(q, k, v, kvs, O=o, workspace=ws), 50)
         ops.flash_attention_v2_splitkv(q, k, v, kvs, *ws)
         S = ws[0].shape[0]
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        # (a) back to back (workspace may sit in the 126 MB L2), (b) L2 flushed before every launch
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda").zero_()
+        # (a) back to back (workspace may sit in the 126 MB L2), (b) L2 flushed before every launch by READING 512 MB
+        # (a write-flush would leave 126 MB of dirty lines whose write-back competes with the timed kernel)
         ms_hot = timed(lambda: ops.flash_attention_v2_combine(ws[0], ws[1], torch.bfloat16, (B, H, L, d), o), 50)
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
         for i in range(20):
-            flush.zero_()
+            flush.view(torch.int64).sum()
             e0[i].record()
             ops.flash_attention_v2_combine(ws[0], ws[1], torch.bfloat16, (B, H, L, d), o)
             e1[i].record()
@@ -360,7 +363,13 @@ def cpu_baseline(workload):
     try:
         B, H, L, d, dt, _ = WORKLOADS[workload]
         threads = os.cpu_count() or 1
-        heads = max(threads, 8)
+        per_head_gflop = flops(1, 1, L, d) / 1e9
+        if per_head_gflop > 40:      # one head alone would take minutes on the host (C4: 137 GFLOP per head)
+            return {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable",
+                    "sample": f"one head of this workload is {per_head_gflop:.0f} GFLOP: too long for a bounded CPU sample"}
+        # ~10-30 s of CPU work: the reference path runs ~0.03 GFLOP/s... measured 0.9 GFLOP/s per thread here
+        heads = int(min(B * H, max(threads, 12.0 * threads / max(per_head_gflop, 1e-3))))
+        heads = int(os.environ.get("FA_BENCH_CPU_HEADS", heads))   # test hook: shrink the CPU sample
         secs, kind, threads = cpu_sample(workload, heads, threads)
         tf = flops(1, heads, L, d) / secs / 1e12
         return {"value": round(tf, 5), "unit": UNIT, "cores": threads, "kind": kind,
@@ -379,7 +388,10 @@ def run_reference(args):
         return
     B, H, L, d, dt, desc = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    heads = max(threads, 8)                 # bounded sample per step: one head per thread
+    per_head_gflop = flops(1, 1, L, d) / 1e9
+    # bounded sample per step (~10 s of CPU work at ~1 GFLOP/s/thread), at most the whole batch, at least one head/thread
+    heads = int(min(B * H, max(threads, 10.0 * threads / max(per_head_gflop, 1e-3))))
+    heads = int(os.environ.get("FA_BENCH_CPU_HEADS", heads))       # test hook: shrink the CPU sample
     steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
     for _ in range(warm):
         cpu_sample(args.workload, heads, threads)

@@ -126,6 +126,7 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = o_accum;
   p.lse_accum = lse_accum;
+  p.o_ptr = O;
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...
@@ -177,6 +178,7 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = nullptr;
   p.lse_accum = nullptr;
+  p.o_ptr = O;
   auto kern = fa::fa_tiled_d_kernel<D, DT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   dim3 grid((L + 127) / 128, BH, T::NSLAB);

@@ -47,7 +47,12 @@ struct FwdParams {
   float scale;       // 1/sqrt(d)
   float* o_accum;    // [n_splits][BH][L][D] fp32, each split normalised by its own l   (SPLIT only)
   float* lse_accum;  // [n_splits][BH][L]    fp32, m/sqrt(d) + ln(l)                     (SPLIT only)
+  void* o_ptr;       // O [BH][L][D] in the storage dtype                                (non-SPLIT)
 };
+
+#ifndef FA_DIRECT_STORE
+#define FA_DIRECT_STORE 0  // 0: O staged in smem + TMA store (ships).  1: registers -> global, frees 32 KB for a 5th K/V
+#endif                     //    ring stage, but the 16-byte row-strided stores cost 11 % at L=1024 for +1 % at L=16384
 
 template <int D, int DT>
 struct FwdTraits {
@@ -66,12 +71,13 @@ struct FwdTraits {
   static constexpr int KPR = SWB / 32;             // MMA K-steps per block row
   static constexpr int TILE_BYTES = NBLK * BLK_BYTES;
   static constexpr int UK = 32 / ES;               // MMA K: 16 (16-bit) / 8 (tf32)
-  static constexpr int NS = (TILE_BYTES >= 32768) ? 4 : 8;  // K/V ring depth
+  static constexpr int NS = (TILE_BYTES >= 32768) ? (FA_DIRECT_STORE ? 5 : 4) : 8;  // K/V ring depth
+  static constexpr int STAGING_BYTES = FA_DIRECT_STORE ? 0 : 2 * BLK_BYTES;
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S = 0, TM_O = 256;
   static_assert(256 + 2 * D <= 512, "S and O accumulators must fit TMEM");
   static constexpr int NUM_BARS = 2 + 2 + 2 * NS + 2 + 4 + 2 + 2;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + 2 * BLK_BYTES + NUM_BARS * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16;
   static constexpr int THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle}
 };
 
@@ -87,8 +93,30 @@ struct FwdTraits {
 #define FA_PREISSUE 0   // 1: issue the next item's first QK^T right behind this item's last PV (helps 1-tile items by ~3 %,
 #endif                  //    costs ~2 % at d=128 / L>=1024 on B200, so off)
 
+#ifndef FA_POLY_MOD
+#define FA_POLY_MOD 4   // N > 0: one element pair in N takes exp2 on the FMA pipes (Cody-Waite + degree-3 polynomial);
+                        // measured on B200: N=4 gives +5 % at d=32, +2 % at d=128 L=1024, N=2/3 no better
+#endif
+
 // Softmax rescale threshold in log2 units (P values stay <= 2^8; exact after the final O / l).
 constexpr float kRescaleThreshold = 8.0f;
+
+// 2^x for a pair of fp32 on the FMA/ALU pipes: n = round(x) via the 1.5*2^23 trick, 2^f on [-0.5, 0.5] by a degree-3
+// minimax polynomial (max relative error 7.5e-5, below the 2^-9 rounding of a bf16/fp16 P and the 2^-11 of tf32),
+// then n is added into the exponent field.  Inputs are <= kRescaleThreshold; anything below -126 flushes to 2^-126.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));          // low mantissa bits = round(x)
+  const float2 r = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));        // float(round(x))
+  const float2 f = __ffma2_rn(r, make_float2(-1.0f, -1.0f), x);                   // x - round(x)
+  float2 q = __ffma2_rn(f, make_float2(0.05517166f, 0.05517166f), make_float2(0.24261113f, 0.24261113f));
+  q = __ffma2_rn(q, f, make_float2(0.69326097f, 0.69326097f));
+  q = __ffma2_rn(q, f, make_float2(0.99992806f, 0.99992806f));
+  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return q;
+}
 
 struct ItemCoord {
   int q_row0, bh, split, kv_begin, kv_end, n_tiles, n_q;
@@ -123,7 +151,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + 2 * TILE_BYTES;
   uint8_t* sOut = sKV + NS * TILE_BYTES;  // [2] one 128-row x 128-B staging block per softmax warpgroup
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * BLK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + T::STAGING_BYTES);
   uint64_t* q_full = bars;              // [2]  TMA -> MMA: Q_i of this item landed
   uint64_t* q_empty = q_full + 2;       // [2]  MMA (commit) -> TMA: every QK_i of this item retired, Q_i may be overwritten
   uint64_t* kv_full = q_empty + 2;      // [NS] TMA -> MMA
@@ -158,7 +186,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      if (!SPLIT) tma_prefetch_desc(&tmO);
+      if (!SPLIT && !FA_DIRECT_STORE) tma_prefetch_desc(&tmO);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, T::TMEM_COLS);
@@ -318,6 +346,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tS = t_lane + T::TM_S + i * BN;
     const uint32_t tO = t_lane + T::TM_O + i * D;
     uint8_t* sO = sOut + i * BLK_BYTES;
+    const uint32_t sO_addr = smem_u32(sO);
     const bool storer = ((warp & 3) == 0) && (lane == 0);
     int nt = 0;  // KV tiles processed (phase of s_full / p_full), across items
     int ni = 0;  // items processed (phase of o_done)
@@ -402,8 +431,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               v.x = fmaf(v.x, p.scale_log2, neg_m);
               v.y = fmaf(v.y, p.scale_log2, neg_m);
 #endif
-              v.x = ex2_approx(v.x);
-              v.y = ex2_approx(v.y);
+              // MUFU does 16 ex2/clk/SM, as many cycles per KV tile as the tensor pipe needs at d=128 and 2-4x more
+              // at d<=64, so every FA_POLY_MOD-th element pair is evaluated on the FMA pipes instead.
+              if (FA_POLY_MOD > 0 && ((x >> 1) % (FA_POLY_MOD > 0 ? FA_POLY_MOD : 1)) == FA_POLY_MOD - 1) {
+                v = exp2_poly2(v);
+              } else {
+                v.x = ex2_approx(v.x);
+                v.y = ex2_approx(v.y);
+              }
 #if FA_PACKED
               lsum[cc] = __fadd2_rn(lsum[cc], v);
 #else
@@ -481,6 +516,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               *reinterpret_cast<float4*>(dst + cc * 32 + x) = v;
             }
         }
+      } else if (FA_DIRECT_STORE) {
+        // Each thread owns one output row: D*ES contiguous bytes written as 16-byte vectors straight from registers.
+        // (A staged TMA store costs 32 KB of smem = one K/V ring stage; the ring stage is worth more at long L.)
+        if (row_g < p.L) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(p.o_ptr) + (size_t(c.bh) * p.L + row_g) * (size_t(D) * T::ES);
+#pragma unroll
+          for (int u = 0; u < D * T::ES / 16; ++u) {
+            uint4 v;
+            if constexpr (DT == DT_F32) {
+              const int e = u * 4;
+              v.x = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 0]) * inv_l);
+              v.y = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 1]) * inv_l);
+              v.z = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 2]) * inv_l);
+              v.w = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 3]) * inv_l);
+            } else {
+              const int e = u * 8;
+              auto pk2 = [&](int ee) {
+                const float a0 = __uint_as_float(o[ee / 32][ee % 32]) * inv_l;
+                const float a1 = __uint_as_float(o[ee / 32][ee % 32 + 1]) * inv_l;
+                return (DT == DT_BF16) ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
+              };
+              v.x = pk2(e + 0);
+              v.y = pk2(e + 2);
+              v.z = pk2(e + 4);
+              v.w = pk2(e + 6);
+            }
+            *reinterpret_cast<uint4*>(dst + u * 16) = v;
+          }
+        }
       } else {
         // One 128-byte column block at a time through this warpgroup's staging block (same 128B swizzle), TMA store.
 #pragma unroll
@@ -510,7 +574,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
             // 128B swizzle: chunk ^= row % 8; 64B swizzle: chunk ^= (row / 2) % 4   (address bits [4,7) ^ [7,10))
             const int sw = (T::SWB == 128) ? (row & 7) : ((row >> 1) & 3);
-            *reinterpret_cast<uint4*>(sO + row * T::SWB + ((u ^ sw) << 4)) = v;
+            st_shared_v4(sO_addr + row * T::SWB + ((u ^ sw) << 4), v);
           }
           fence_proxy_async_smem();
           named_bar_sync(1 + i, 128);
@@ -521,7 +585,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
     }
-    if (!SPLIT && storer) tma_store_wait_read_all();  // smem must outlive the last store's read
+    if (!SPLIT && !FA_DIRECT_STORE && storer) tma_store_wait_read_all();  // smem must outlive the last store's read
   }
 
   tc_fence_before();

@@ -69,6 +69,11 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   return r;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t smem_addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -149,12 +149,22 @@ def run_ours(args):
         return float(t.item())
 
     # ---- synthetic inputs: NSETS rotating input sets, each (3 inputs + output) = 4*B*H*L*d*esize bytes
-    tensor_bytes = B * H * L * d * esize
+    # weak scaling (default): every rank runs the whole batch.  --scaling strong: the B*H heads are sharded by
+    # contiguous slices (sharding.head_range), the north_star's (batch, head) partition; still no collective.
+    strong = args.scaling == "strong" and world > 1
+    total_flops = flops(B, H, L, d) * (1 if strong else world)
+    if strong:
+        from exploring_flash_attention_b200.sharding import head_range
+        hb, he = head_range(B * H, rank, world)
+        Bl, Hl = 1, he - hb
+    else:
+        Bl, Hl = B, H
+    tensor_bytes = Bl * Hl * L * d * esize
     nsets = 3 if tensor_bytes * 4 < (1 << 30) else 1
     g = torch.Generator(device="cpu").manual_seed(42 + rank)
     sets = []
     for _ in range(nsets):
-        q, k, v = ((torch.rand((B, H, L, d), generator=g, dtype=torch.float32) * 2 - 1).to(dtype).cuda() for _ in range(3))
+        q, k, v = ((torch.rand((Bl, Hl, L, d), generator=g, dtype=torch.float32) * 2 - 1).to(dtype).cuda() for _ in range(3))
         sets.append((q, k, v, torch.empty_like(q)))
     variant = 1 if args.workload in ("c2", "c5") else 0
 
@@ -177,7 +187,7 @@ def run_ours(args):
         sampler.pause()
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    value = world * flops(B, H, L, d) / (ms_step * 1e-3) / 1e12
+    value = total_flops / (ms_step * 1e-3) / 1e12
     clock_note = "sampled during the timed region"
     if sampler and len(sampler.samples) < 5:
         # timed region too short for NVML polling: replay the same step for ~0.4 s (untimed) and sample under that load
@@ -196,14 +206,14 @@ def run_ours(args):
     # one kernel launch per step, launches back to back on one stream: the kernel's average duration over the timed
     # region IS ms_step (a second timing pass after the clock-sampling replay would run power-capped and read lower)
     per_launch_ms = ms_step
-    achieved = flops(B, H, L, d) / (per_launch_ms * 1e-3) / 1e12
+    achieved = flops(Bl, Hl, L, d) / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0),
                 "unit": "TFLOP/s", "frac": round(achieved / (pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0)), 4),
                 "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "kernel": "fa_fwd_kernel" if d <= 128 else "fa_tiled_d_kernel",
                 "peak_source": pk["source"] + (", burst bf16 cuBLAS" if dt != "f32" else ", burst bf16 cuBLAS / 2 (tf32)"),
                 "frac_of_sustained": round(achieved / (pk["bf16_tflops_sustained"] / (2.0 if dt == "f32" else 1.0)), 4)
                 if pk["bf16_tflops_sustained"] else None,
-                "algorithmic_flops_per_launch": flops(B, H, L, d)}
+                "algorithmic_flops_per_launch": flops(Bl, Hl, L, d)}
 
     # ---- end to end through the C ABI with HOST buffers (H2D x3 + kernel + D2H inside the timed region)
     qh, kh, vh = (t.cpu().pin_memory() for t in sets[0][:3])
@@ -218,7 +228,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     barrier()
-    e2e = {"value": round(world * flops(B, H, L, d) / (e2e_ms * 1e-3) / 1e12, 3), "unit": UNIT,
+    e2e = {"value": round(total_flops / (e2e_ms * 1e-3) / 1e12, 3), "unit": UNIT,
            "h2d_bytes_per_step": 3 * tensor_bytes, "d2h_bytes_per_step": tensor_bytes, "ms_per_step": round(e2e_ms, 3),
            "steps": e2e_steps, "api": "fa_forward_host (include/fa_b200.h)"}
 
@@ -230,9 +240,9 @@ def run_ours(args):
         cpu_base = cpu_baseline(args.workload) if world == 1 else None
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": dt, "data": "synthetic U[-1,1) seed 42 (random Q,K,V; no weights on this path)",
-            "config": {"workload": desc, "B": B, "H": H, "L": L, "d": d, "per_gpu_batch": f"B{B} H{H}",
+            "config": {"workload": desc, "B": B, "H": H, "L": L, "d": d, "per_gpu_batch": f"{Bl * Hl} of {B * H} heads" if strong else f"B{B} H{H}",
                        "sharding": "independent (batch,head) work per GPU, no collective",
                        "l2": f"{nsets} rotating input sets, {4 * tensor_bytes * nsets / 1e6:.0f} MB working set > 126 MB L2, no flush"},
             "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
@@ -421,6 +431,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU runs the whole batch; strong: the batch's heads are sharded across the GPUs")
     ap.add_argument("--no-also", dest="also", action="store_false", help="skip the side measurements (C4/C1/C3)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

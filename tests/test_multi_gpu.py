@@ -1,0 +1,55 @@
+"""GPU, 2+ devices (skipped on a 1-GPU box): heads sharded over ranks, each rank runs the CUDA path on its slice, the
+slices are all-gathered over NCCL and the assembled tensor is checked against the oracle."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from exploring_flash_attention_b200 import ops
+    from exploring_flash_attention_b200.sharding import gather_heads, shard_heads
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    B, H, L, d = 1, 5, 640, 128                       # 5 heads over 2 ranks: uneven shards
+    g = torch.Generator().manual_seed(42)
+    Q, K, V = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
+    qs, ks, vs = (shard_heads(x, rank, world).contiguous().cuda() for x in (Q, K, V))
+    local = ops.flash_attention_v1(qs, ks, vs, sync=True)
+    full = gather_heads(local, B * H)
+    dist.barrier()
+    if rank == 0:
+        q.put((full.float().cpu().numpy(), Q.float().numpy(), K.float().numpy(), V.float().numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_head_sharding_nccl_gather():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import reference
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, Q, K, V = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = reference.naive_attention_batched_f64(Q, K, V)
+    assert full.shape == ref.shape
+    assert np.abs(full - ref).max() <= 2e-3

@@ -181,7 +181,9 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   p.o_ptr = O;
   auto kern = fa::fa_tiled_d_kernel<D, DT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-  dim3 grid((L + 127) / 128, BH, T::NSLAB);
+  const long long blocks = (long long)((L + 127) / 128) * BH * T::NSLAB;
+  if (blocks > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-tile, slab) blocks");
+  dim3 grid((unsigned)blocks);
   kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;

@@ -11,7 +11,7 @@
 // B200 mapping (why this is a different kernel from K1): a 128-row O accumulator at d = 512 would need all 512 TMEM
 // columns, leaving nothing for S.  So one CTA owns 128 query rows x one 256-wide slab of the output head dim:
 //   TMEM  S[0] [0,128)  S[1] [128,256)  O [256,512)            (S double-buffered: QK(j+1) overlaps softmax(j))
-//   grid  (ceil(L/128), B*H, D/256);  for d = 512 the two slabs of a q-tile recompute S (QK^T is 2/3 of the MMA work
+//   grid  1-D over (head, q-tile, slab), slab fastest;  for d = 512 the two slabs of a q-tile recompute S (QK^T is 2/3 of the MMA work
 //         there; documented cost of fitting TMEM — the roofline uses algorithmic FLOPs only).
 //   smem  Q resident as D/64 swizzled [128 x 128 B] blocks; one ring of 16 KB stages streams, per KV tile,
 //         D/64 K chunks ([128 keys x 64 d], K-major B operand) then 4 V chunks ([128 keys x 64 d_v], MN-major B operand).
@@ -68,9 +68,12 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * BM;
-  const int bh = blockIdx.y;
-  const int slab = blockIdx.z;                 // which 256-wide slab of the output head dim
+  // 1-D grid, slab fastest then q tile then head: the slabs of one q-tile (which recompute the same S from the same
+  // K chunks) and the q-tiles of one head run on neighbouring SMs at the same time and share K/V through L2.
+  const int slab = blockIdx.x % T::NSLAB;      // which 256-wide slab of the output head dim
+  const int n_qtiles = (p.L + BM - 1) / BM;
+  const int q_row0 = ((blockIdx.x / T::NSLAB) % n_qtiles) * BM;
+  const int bh = blockIdx.x / (T::NSLAB * n_qtiles);
   const int n_tiles = (p.L + BN - 1) / BN;
 
   if (warp == 5 && lane == 0) {

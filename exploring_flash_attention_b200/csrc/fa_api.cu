@@ -223,6 +223,10 @@ struct HostStaging {
   size_t bytes = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  static constexpr int kChunks = 8;       // head chunks in flight through the H2D / compute / D2H pipeline
+  cudaStream_t stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d[kChunks] = {}, ev_comp[kChunks] = {};
+  bool streams_ready = false;
   std::mutex mu;
 } g_stage;
 
@@ -352,34 +356,63 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
     for (auto& b : g_stage.buf) FA_CUDA_TRY(cudaMalloc(&b, bytes));
     g_stage.bytes = bytes;
   }
-  cudaStream_t s = nullptr;
-  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[0], Qh, bytes, cudaMemcpyHostToDevice, s));
-  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[1], Kh, bytes, cudaMemcpyHostToDevice, s));
-  FA_CUDA_TRY(cudaMemcpyAsync(g_stage.buf[2], Vh, bytes, cudaMemcpyHostToDevice, s));
-  int rc;
-  if (variant == 0) {
-    rc = fa_v1_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, dtype, s);
-  } else if (variant == 1) {
-    const int dt = d >= 64 ? 64 : d;
-    rc = fa_v1_tiled_d_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, dt, dt, dtype, s);
-  } else if (variant == 2) {
-    const size_t need = fa_v2_workspace_bytes(B, H, L, d, kv_per_split);
-    if (need == 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
-    if (need > g_stage.ws_bytes) {
+  if (variant < 0 || variant > 2) return fail(FA_ERR_SHAPE, "variant must be 0 (V1), 1 (tiled-d) or 2 (V2)");
+  // Heads are independent, so the batch is pipelined in head chunks over three streams: while chunk c computes, chunk
+  // c+1 is on the H2D copy engine and chunk c-1 on the D2H engine (PCIe is full duplex).  The reference drivers copy,
+  // launch and copy back strictly in sequence (flash_attention_v1/CUDA/driver.cu:184-247).
+  if (!g_stage.streams_ready) {
+    for (auto& st : g_stage.stream) FA_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : g_stage.ev_h2d) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_stage.ev_comp) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_stage.streams_ready = true;
+  }
+  cudaStream_t s_h2d = g_stage.stream[0], s_comp = g_stage.stream[1], s_d2h = g_stage.stream[2];
+  const int BH = B * H;
+  const int n_chunks = BH < HostStaging::kChunks ? BH : HostStaging::kChunks;
+  const size_t head_bytes = size_t(L) * d * elem_size(dtype);
+  size_t ws_need = 0;
+  if (variant == 2) {
+    const int max_heads = (BH + n_chunks - 1) / n_chunks;
+    ws_need = fa_v2_workspace_bytes(1, max_heads, L, d, kv_per_split);
+    if (ws_need == 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
+    if (ws_need > g_stage.ws_bytes) {
       if (g_stage.ws) cudaFree(g_stage.ws);
       g_stage.ws = nullptr;
       g_stage.ws_bytes = 0;
-      FA_CUDA_TRY(cudaMalloc(&g_stage.ws, need));
-      g_stage.ws_bytes = need;
+      FA_CUDA_TRY(cudaMalloc(&g_stage.ws, ws_need));
+      g_stage.ws_bytes = ws_need;
     }
-    rc = fa_v2_forward(g_stage.buf[0], g_stage.buf[1], g_stage.buf[2], g_stage.buf[3], B, H, L, d, kv_per_split, dtype,
-                       g_stage.ws, g_stage.ws_bytes, s);
-  } else {
-    return fail(FA_ERR_SHAPE, "variant must be 0 (V1), 1 (tiled-d) or 2 (V2)");
   }
-  if (rc != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(Oh, g_stage.buf[3], bytes, cudaMemcpyDeviceToHost, s));
-  FA_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int h0 = int((long long)BH * c / n_chunks), h1 = int((long long)BH * (c + 1) / n_chunks);
+    const int nh = h1 - h0;
+    if (nh == 0) continue;
+    const size_t off = size_t(h0) * head_bytes, cb = size_t(nh) * head_bytes;
+    char *dQ = static_cast<char*>(g_stage.buf[0]) + off, *dK = static_cast<char*>(g_stage.buf[1]) + off;
+    char *dV = static_cast<char*>(g_stage.buf[2]) + off, *dO = static_cast<char*>(g_stage.buf[3]) + off;
+    FA_CUDA_TRY(cudaMemcpyAsync(dQ, static_cast<const char*>(Qh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_CUDA_TRY(cudaMemcpyAsync(dK, static_cast<const char*>(Kh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_CUDA_TRY(cudaMemcpyAsync(dV, static_cast<const char*>(Vh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_CUDA_TRY(cudaEventRecord(g_stage.ev_h2d[c], s_h2d));
+    FA_CUDA_TRY(cudaStreamWaitEvent(s_comp, g_stage.ev_h2d[c], 0));
+    int rc;
+    if (variant == 0) {
+      rc = fa_v1_forward(dQ, dK, dV, dO, 1, nh, L, d, dtype, s_comp);
+    } else if (variant == 1) {
+      const int dt = d >= 64 ? 64 : d;
+      rc = fa_v1_tiled_d_forward(dQ, dK, dV, dO, 1, nh, L, d, dt, dt, dtype, s_comp);
+    } else {
+      rc = fa_v2_forward(dQ, dK, dV, dO, 1, nh, L, d, kv_per_split, dtype, g_stage.ws, g_stage.ws_bytes, s_comp);
+    }
+    if (rc != FA_OK) {
+      cudaDeviceSynchronize();
+      return rc;
+    }
+    FA_CUDA_TRY(cudaEventRecord(g_stage.ev_comp[c], s_comp));
+    FA_CUDA_TRY(cudaStreamWaitEvent(s_d2h, g_stage.ev_comp[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(Oh) + off, dO, cb, cudaMemcpyDeviceToHost, s_d2h));
+  }
+  FA_CUDA_TRY(cudaStreamSynchronize(s_d2h));
   return FA_OK;
 }
 

@@ -49,9 +49,15 @@ def load() -> ctypes.CDLL:
         return _lib
     path = Path(LIB_PATH)
     if not path.exists():
-        raise RuntimeError(
-            f"{path} is missing: build it with `python -m exploring_flash_attention_b200._build` "
-            "(or __graft_entry__.build()). This package has no CPU fallback.")
+        # Not a fallback: the same CUDA library, compiled in-tree on first use when a checkout has no built artefact yet.
+        try:
+            from ._build import build
+            build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                f"{path} is missing and could not be built ({e}); build it with "
+                "`python -m exploring_flash_attention_b200._build` (or __graft_entry__.build()). "
+                "This package has no CPU fallback.") from e
     lib = ctypes.CDLL(str(path))
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

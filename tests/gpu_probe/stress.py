@@ -1,0 +1,51 @@
+"""Randomised parity stress (dev tool): random shapes / dtypes / variants vs a float64 torch evaluation, with the
+persistent kernel seeing many different item counts, ragged tails and split sizes.  python tests/gpu_probe/stress.py [seconds]"""
+import random
+import sys
+import time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+import torch
+from exploring_flash_attention_b200 import ops
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+rng = random.Random(1234)
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-3, torch.float16: 2e-3}
+t_end = time.time() + budget
+n = 0
+worst = {}
+while time.time() < t_end:
+    dtype = rng.choice([torch.bfloat16, torch.float16, torch.float32])
+    d = rng.choice([32, 64] if dtype == torch.float32 else [32, 64, 128, 128, 256, 512])
+    L = rng.choice([1, 7, 64, 127, 128, 129, 255, 256, 257, 300, 511, 640, 1000, 1024, 1500, 2048, 3000])
+    if d >= 256:
+        L = min(L, 1024)
+    BH = rng.choice([1, 2, 3, 5, 37, 149, 300]) if L <= 300 else rng.choice([1, 2, 3, 5, 19])
+    variant = rng.choice(["v1", "v1", "v2"]) if d <= 128 else "td"
+    g = torch.Generator().manual_seed(n)
+    Q, K, V = ((torch.rand((1, BH, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
+    if variant == "v1":
+        O = ops.flash_attention_v1(Q, K, V, sync=True)
+        tag = "v1"
+    elif variant == "td":
+        O = ops.flash_attention_v1_tiled_d(Q, K, V, sync=True)
+        tag = "td"
+    else:
+        kvs = rng.choice([8, 64, 100, 128, 256, 1000])
+        O = ops.flash_attention_v2(Q, K, V, kvs, sync=True)
+        tag = f"v2/{kvs}"
+    nh = min(BH, 4)
+    idx = torch.tensor(sorted(rng.sample(range(BH), nh)), device="cuda")
+    q, k, v = (x[0, idx].double() for x in (Q, K, V))
+    ref = torch.softmax(q @ k.transpose(-1, -2) / d ** 0.5, -1) @ v
+    err = (O[0, idx].double() - ref).abs().max().item()
+    key = (str(dtype), d)
+    worst[key] = max(worst.get(key, 0.0), err)
+    # tiny L gives O(1) outputs: allow for the storage type's own output rounding (2^-9 relative for bf16, 2^-12 fp16)
+    out_round = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11, torch.float32: 2.0 ** -11}[dtype] * ref.abs().max().item()
+    if not (err <= TOL[dtype] + out_round) or torch.isnan(O).any():
+        print(f"FAIL case {n}: {tag} dtype={dtype} BH={BH} L={L} d={d} err={err}", flush=True)
+        sys.exit(1)
+    n += 1
+print(f"stress OK: {n} random cases in {budget:.0f} s; worst max-abs error per (dtype, d): "
+      + ", ".join(f"{k[0].split('.')[-1]}/d{k[1]}={v:.1e}" for k, v in sorted(worst.items())))

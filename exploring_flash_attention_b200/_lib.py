@@ -20,6 +20,7 @@ SYMBOLS = {
     "fa_last_error": (c_char_p, []),
     "fa_device_sm_count": (c_int, []),
     "fa_v1_forward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    "fa_v1_forward_ex": (c_int, [c_void_p] * 5 + [c_int] * 5 + [ctypes.c_uint, c_void_p]),
     "fa_v1_tiled_d_forward": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "fa_v2_num_splits": (c_int, [c_int, c_int]),
     "fa_v2_workspace_bytes": (c_size_t, [c_int] * 5),

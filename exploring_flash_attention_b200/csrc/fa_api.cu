@@ -101,7 +101,7 @@ int check_common(const void* Q, const void* K, const void* V, const void* O, int
 
 template <int D, int DT, bool SPLIT>
 int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int kv_per_split, int n_splits,
-               float* o_accum, float* lse_accum, cudaStream_t stream) {
+               float* o_accum, float* lse_accum, cudaStream_t stream, float* lse_out = nullptr, int causal = 0) {
   using T = fa::FwdTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
@@ -127,6 +127,8 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.o_accum = o_accum;
   p.lse_accum = lse_accum;
   p.o_ptr = O;
+  p.lse_out = SPLIT ? nullptr : lse_out;
+  p.causal = SPLIT ? 0 : causal;
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...
@@ -140,10 +142,11 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
 
 template <bool SPLIT>
 int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
-                 int kv_per_split, int n_splits, float* o_accum, float* lse_accum, cudaStream_t s) {
+                 int kv_per_split, int n_splits, float* o_accum, float* lse_accum, cudaStream_t s,
+                 float* lse_out = nullptr, int causal = 0) {
 #define FA_CASE(DD, DTT)                                                                                         \
   if (d == DD && dtype == DTT)                                                                                   \
-    return launch_fwd<DD, DTT, SPLIT>(Q, K, V, O, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s);
+    return launch_fwd<DD, DTT, SPLIT>(Q, K, V, O, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s, lse_out, causal);
   FA_CASE(128, fa::DT_BF16)
   FA_CASE(64, fa::DT_BF16)
   FA_CASE(128, fa::DT_F16)
@@ -179,6 +182,8 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   p.o_accum = nullptr;
   p.lse_accum = nullptr;
   p.o_ptr = O;
+  p.lse_out = nullptr;
+  p.causal = 0;
   auto kern = fa::fa_tiled_d_kernel<D, DT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   const long long blocks = (long long)((L + 127) / 128) * BH * T::NSLAB;
@@ -249,6 +254,16 @@ int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, i
   if (rc != FA_OK) return rc;
   if (d > 128) return fa_v1_tiled_d_forward(Q, K, V, O, B, H, L, d, d >= 64 ? 64 : d, d >= 64 ? 64 : d, dtype, stream);
   return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int L, int d,
+                     int dtype, unsigned flags, void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
+  if (d > 128) return fail(FA_ERR_UNSUPPORTED_D, "LSE output / causal masking are served by the fused-tile kernel only (d <= 128)");
+  return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
+                             LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0);
 }
 
 int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,

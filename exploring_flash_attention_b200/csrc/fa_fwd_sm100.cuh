@@ -48,6 +48,8 @@ struct FwdParams {
   float* o_accum;    // [n_splits][BH][L][D] fp32, each split normalised by its own l   (SPLIT only)
   float* lse_accum;  // [n_splits][BH][L]    fp32, m/sqrt(d) + ln(l)                     (SPLIT only)
   void* o_ptr;       // O [BH][L][D] in the storage dtype                                (non-SPLIT)
+  float* lse_out;    // optional [BH][L] fp32: log-sum-exp of the scaled scores of each row      (non-SPLIT, may be null)
+  int causal;        // != 0: query row r attends to keys 0..r only                            (non-SPLIT)
 };
 
 #ifndef FA_DIRECT_STORE
@@ -89,9 +91,8 @@ struct FwdTraits {
 #define FA_PACKED 1     // 1: packed fp32x2 FFMA2 / FADD2 for the scale-subtract and the row sum (halves their issue slots)
 #endif
 
-#ifndef FA_PREISSUE
-#define FA_PREISSUE 0   // 1: issue the next item's first QK^T right behind this item's last PV (helps 1-tile items by ~3 %,
-#endif                  //    costs ~2 % at d=128 / L>=1024 on B200, so off)
+// (Tried and dropped: issuing the next item's first QK^T right behind this item's last PV — +3 % for 1-tile items,
+//  -2 % at d=128 / L>=1024.)
 
 #ifndef FA_POLY_MOD
 #define FA_POLY_MOD 4   // N > 0: one element pair in N takes exp2 on the FMA pipes (Cody-Waite + degree-3 polynomial);
@@ -120,13 +121,21 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 
 struct ItemCoord {
   int q_row0, bh, split, kv_begin, kv_end, n_tiles, n_q;
+  int nt[2];  // KV tiles Q tile i actually needs (causal: up to its diagonal tile); n_tiles = the larger of the two
 };
 
 template <bool SPLIT>
 __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   ItemCoord c;
-  const int qp = item % p.n_qpairs;
-  const int rest = item / p.n_qpairs;
+  int qp = item % p.n_qpairs;
+  int rest = item / p.n_qpairs;
+  if (!SPLIT && p.causal) {
+    // Causal items grow with the q-pair index.  Order ALL items longest-first (q-pair descending, head fastest) so the
+    // static round-robin over CTAs is an LPT schedule; head-major order would hand every CTA the same q-pair index
+    // whenever gridDim.x is a multiple of n_qpairs.
+    qp = p.n_qpairs - 1 - item / p.BH;
+    rest = item % p.BH;
+  }
   c.split = SPLIT ? rest % p.n_splits : 0;
   c.bh = SPLIT ? rest / p.n_splits : rest;
   c.q_row0 = qp * 256;
@@ -134,6 +143,12 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   c.kv_end = SPLIT ? min(p.L, c.kv_begin + p.kv_per_split) : p.L;
   c.n_tiles = (c.kv_end - c.kv_begin + 127) / 128;
   c.n_q = (p.L - c.q_row0 > 128) ? 2 : 1;
+  c.nt[0] = c.nt[1] = c.n_tiles;
+  if (!SPLIT && p.causal) {
+    c.nt[0] = min(c.n_tiles, c.q_row0 / 128 + 1);
+    c.nt[1] = min(c.n_tiles, c.q_row0 / 128 + 2);
+    c.n_tiles = c.n_q > 1 ? c.nt[1] : c.nt[0];
+  }
   return c;
 }
 
@@ -264,38 +279,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         int tt = 0;            // K/V tiles consumed so far (ring position), across items
         int nt[2] = {0, 0};    // KV tiles processed for Q tile i (phase of s_full / p_full), across items
         int ni[2] = {0, 0};    // items processed for Q tile i (phase of q_full / o_done / o_free)
-        bool pre[2] = {false, false};  // QK_i(0) of the coming item was already issued behind the previous item's last PV_i
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const ItemCoord c = decode_item<SPLIT>(item, p);
           const int t0 = tt;   // ring index of K_0 of this item
-          const int item_n = item + gridDim.x;
-          const bool has_item_n = item_n < p.n_items;
-          ItemCoord cn = c;
-          if (has_item_n) cn = decode_item<SPLIT>(item_n, p);
-          const int tn0 = t0 + 2 * c.n_tiles;  // ring index of the next item's K_0
-
-          // first QK^T of a Q tile: S_i = Q_i K_0^T (for the tiles not pre-issued at the end of the previous item)
-          auto first_qk = [&](int i, int ring_idx, int q_phase, int n_tiles_of_item) {
-            mbar_wait(&kv_full[ring_idx % NS], (ring_idx / NS) & 1);
-            mbar_wait(&q_full[i], q_phase & 1);
-            tc_fence_after();
-            qk(i, ring_idx % NS);
-            tc_commit(&s_full[i]);
-            if (n_tiles_of_item == 1) tc_commit(&q_empty[i]);
-          };
+          mbar_wait(&kv_full[t0 % NS], (t0 / NS) & 1);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {  // compile-time i: the per-tile counters stay in registers
-            if (i >= c.n_q || pre[i]) continue;
-            first_qk(i, t0, ni[i], c.n_tiles);
+            if (i >= c.n_q) continue;
+            mbar_wait(&q_full[i], ni[i] & 1);
+            tc_fence_after();
+            qk(i, t0 % NS);
+            tc_commit(&s_full[i]);
+            if (c.nt[i] == 1) tc_commit(&q_empty[i]);
           }
           tc_commit(&kv_empty[t0 % NS]);  // K_0: both QK(0) are issued by now
           for (int j = 0; j < c.n_tiles; ++j) {
             const int tv = t0 + 2 * j + 1, tk = t0 + 2 * j + 2;
-            const bool has_next = (j + 1 < c.n_tiles);
+            bool k_waited = false;
             mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              if (i >= c.n_q) continue;
+              if (i >= c.n_q || j >= c.nt[i]) continue;  // causal: tile 0 stops one KV tile before tile 1
               if (j == 0 && ni[i] > 0) {
                 // PV_i(0) overwrites O_i: the previous item's epilogue must have read it out of TMEM
                 mbar_wait(&o_free[i], (ni[i] - 1) & 1);
@@ -311,27 +315,23 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
               }
               ++nt[i];
-              if (has_next) {
-                if (i == 0) {
+              if (j + 1 < c.nt[i]) {
+                if (!k_waited) {
                   mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
                   tc_fence_after();
+                  k_waited = true;
                 }
                 qk(i, tk % NS);
                 tc_commit(&s_full[i]);
-                if (j + 2 == c.n_tiles) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
+                if (j + 2 == c.nt[i]) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
               } else {
                 tc_commit(&o_done[i]);
-                // Keep the tile stream going across the item boundary: the next item's S_i = Q_i' K_0'^T follows
-                // this item's last PV_i exactly like QK_i(j+1) follows PV_i(j) inside an item.
-                pre[i] = FA_PREISSUE && has_item_n && i < cn.n_q;
-                if (pre[i]) first_qk(i, tn0, ni[i] + 1, cn.n_tiles);
               }
             }
             tc_commit(&kv_empty[tv % NS]);
-            if (has_next) tc_commit(&kv_empty[tk % NS]);
+            if (j + 1 < c.n_tiles) tc_commit(&kv_empty[tk % NS]);
           }
-          if (c.n_q < 2) pre[1] = false;
-          tt = tn0;
+          tt = t0 + 2 * c.n_tiles;
           ++ni[0];
           if (c.n_q > 1) ++ni[1];
         }
@@ -357,7 +357,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       float m_used = -CUDART_INF_F;
       float l = 0.f;
 
-      for (int j = 0; j < c.n_tiles; ++j, ++nt) {
+      const int my_tiles = c.nt[i];
+      const int row_q = c.q_row0 + i * BM + row;   // my query row inside the head
+      for (int j = 0; j < my_tiles; ++j, ++nt) {
         mbar_wait(&s_full[i], nt & 1);
         tc_fence_after();
         uint32_t s[4][32];
@@ -367,9 +369,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
         // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
         // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
-        const int valid = c.kv_end - (c.kv_begin + j * BN);
+        // valid = number of leading columns of this tile my row may attend to: the ragged end of the key range and,
+        // when causal, the diagonal (key index <= query row); only the last tile of a row can be cut.
+        int valid = c.kv_end - (c.kv_begin + j * BN);
+        if (!SPLIT && p.causal) valid = min(valid, row_q - j * BN + 1);
         float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
-        if (valid >= BN) {
+        if (__all_sync(0xffffffffu, valid >= BN)) {
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
             mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
@@ -502,6 +507,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_arrive(&o_free[i]);  // O_i is in registers: the MMA warp may start the next item's PV_i
       const float inv_l = 1.0f / l;
       const int row_g = c.q_row0 + i * BM + row;
+      if (!SPLIT && p.lse_out != nullptr && row_g < p.L)
+        p.lse_out[size_t(c.bh) * p.L + row_g] = m_used * p.scale + __logf(l);
       if constexpr (SPLIT) {
         if (row_g < p.L) {
           const size_t ridx = (size_t(c.split) * p.BH + c.bh) * p.L + row_g;

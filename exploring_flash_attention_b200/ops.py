@@ -43,6 +43,23 @@ def flash_attention_v1(Q, K, V, O=None, sync: bool = False):
     return O
 
 
+def flash_attention_v1_ex(Q, K, V, O=None, causal: bool = False, return_lse: bool = False, sync: bool = False):
+    """Fused-tile kernel with the extras the reference lists as future work: causal masking and the per-row
+    log-sum-exp (natural log of sum_j exp(q.k_j/sqrt(d))). Returns O, or (O, LSE [B,H,L] fp32)."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if O is None:
+        O = torch.empty_like(Q)
+    lse = torch.empty((B, H, L), dtype=torch.float32, device=Q.device) if return_lse else None
+    lib = _lib.load()
+    _lib.check(lib.fa_v1_forward_ex(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                    lse.data_ptr() if return_lse else None, B, H, L, d, _DTYPES[Q.dtype],
+                                    1 if causal else 0, _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return (O, lse) if return_lse else O
+
+
 def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: int = 32, sync: bool = False):
     """Tiled-d variant (head dims up to 512); d_tile_* are validated streaming hints."""
     Q, K, V = _prep(Q, K, V)

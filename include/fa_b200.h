@@ -52,6 +52,15 @@ int fa_device_sm_count(void);
 int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int dtype,
                   void* stream /* cudaStream_t */);
 
+/* ---- V1, extended (the reference lists "dynamic sequence lengths and causal masking" as future work,
+ * flash_attention_v1/README_v1.md:169).  Same kernel as fa_v1_forward plus:
+ *   LSE   optional [B*H*L] fp32 output: log(sum_j exp(q_i.k_j / sqrt(d))) per query row (NULL to skip);
+ *   flags FA_FLAG_CAUSAL: query row i attends to keys 0..i only (KV tiles above the diagonal are never loaded).
+ * d <= 128 only. */
+#define FA_FLAG_CAUSAL 1u
+int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int L, int d,
+                     int dtype, unsigned flags, void* stream);
+
 /* ---- V1 tiled-d -----------------------------------------------------------------------------
  * Replaces  void flash_attention_v1[_opt](..., int d_runtime, int d_tile_qk_runtime, int d_tile_v_runtime)
  *           flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:312-354, flash_attention_v1_opt.h:448-490.

@@ -27,6 +27,21 @@ def naive_attention_f64(Q, K, V):
                            np.asarray(V, dtype=np.float64))
 
 
+def naive_attention_ex_f64(Q, K, V, causal=False):
+    """Extended oracle for SURVEY.md §8(f)-1 (not in the reference, which defers causal masking,
+    flash_attention_v1/README_v1.md:169): same math as naive_attention with an optional causal mask (row i sees keys
+    0..i) and the per-row log-sum-exp of the scaled scores.  [L,d] float64 -> (O [L,d], LSE [L])."""
+    Q, K, V = (np.asarray(x, dtype=np.float64) for x in (Q, K, V))
+    L, d = Q.shape
+    s = (Q @ K.T) * (1.0 / np.sqrt(d))
+    if causal:
+        s = np.where(np.tril(np.ones((L, L), dtype=bool)), s, -np.inf)
+    m = s.max(axis=1, keepdims=True)
+    p = np.exp(s - m)
+    l = p.sum(axis=1, keepdims=True)
+    return (p / l) @ V, (m + np.log(l))[:, 0]
+
+
 def naive_attention_batched_f64(Q, K, V, heads=None, rows=None):
     """[B,H,L,d] (or [BH,L,d]) inputs -> float64 outputs for the selected flat head indices and query rows.
 

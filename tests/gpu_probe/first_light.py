@@ -35,6 +35,8 @@ CASES = [
     ("C1_full", "v1", 32, 8, 1024, 32, "f32", 0),
     ("C3_full", "v2", 32, 8, 256, 64, "bf16", 64),
     ("C4_slice", "v1", 1, 16, 16384, 128, "bf16", 0),
+    ("C4_slice_causal", "causal", 1, 16, 16384, 128, "bf16", 0),
+    ("C2_causal", "causal", 32, 8, 1024, 128, "bf16", 0),
     ("td_d256", "v1", 1, 2, 512, 256, "bf16", 0),
     ("td_d512", "v1", 1, 2, 512, 512, "bf16", 0),
     ("td_d256_big", "v1", 4, 8, 4096, 256, "bf16", 0),
@@ -55,7 +57,9 @@ def run_case(case):
         K = K * 12.0
         kvs = 0
     Q, K, V = (x.to(dtype).cuda() for x in (Q, K, V))
-    if variant == "v1":
+    if variant == "causal":
+        fn = lambda: ops.flash_attention_v1_ex(Q, K, V, causal=True)
+    elif variant == "v1":
         fn = lambda: ops.flash_attention_v1(Q, K, V)
     else:
         ws = ops.v2_workspace(B, H, L, d, kvs, Q.device)
@@ -67,6 +71,8 @@ def run_case(case):
     Qd, Kd, Vd = (x.reshape(B * H, L, d)[:nh].double() for x in (Q, K, V))
     rows = min(L, 2048)
     S = torch.einsum("hqd,hkd->hqk", Qd[:, :rows], Kd) / (d ** 0.5)
+    if variant == "causal":
+        S = S.masked_fill(torch.ones(rows, L, device=S.device, dtype=torch.bool).triu(1), float("-inf"))
     ref = torch.softmax(S, dim=-1) @ Vd
     got = O.reshape(B * H, L, d)[:nh, :rows].double()
     err = (got - ref).abs().max().item()

@@ -125,3 +125,15 @@ def test_driver_inputs_and_cpu_reference_known_answers(d, known):
     Q, K, V = cpu.driver_inputs(32, 8, 1024, d)
     O = cpu.standard_attention_cpu(Q, K, V, head_begin=0, head_end=1)
     np.testing.assert_allclose(O[0, 0, 0, :3].astype(np.float64), known, rtol=0, atol=6e-8)
+
+
+def test_extended_oracle_reduces_to_reference_and_masks():
+    Q, K, V = qkv(7, 50, 16, np.float64)
+    O, lse = reference.naive_attention_ex_f64(Q, K, V, causal=False)
+    np.testing.assert_allclose(O, reference.naive_attention(Q, K, V), atol=1e-14)
+    s = (Q @ K.T) / 4.0
+    np.testing.assert_allclose(lse, np.log(np.exp(s).sum(1)), atol=1e-12)
+    Oc, lsec = reference.naive_attention_ex_f64(Q, K, V, causal=True)
+    np.testing.assert_allclose(Oc[0], V[0], atol=1e-15)                       # row 0 sees key 0 only
+    np.testing.assert_allclose(Oc[-1], O[-1], atol=1e-14)                     # last row sees everything
+    np.testing.assert_allclose(lsec[3], np.log(np.exp(s[3, :4]).sum()), atol=1e-12)

@@ -299,3 +299,36 @@ def _fp16_d32_supported(ops):
         return True
     except FlashAttentionError:
         return False
+
+
+@pytest.mark.parametrize("B,H,L,d,dtype", [
+    (1, 2, 512, 128, torch.bfloat16), (2, 2, 333, 64, torch.bfloat16), (1, 3, 1000, 128, torch.float16),
+    (1, 2, 700, 32, torch.float32), (1, 2, 129, 64, torch.float32), (1, 2, 100, 32, torch.float16), (1, 1, 1, 128, torch.bfloat16),
+    (1, 5, 2048, 128, torch.bfloat16),
+])
+def test_causal_and_lse_match_extended_oracle(ops, B, H, L, d, dtype):
+    """causal mask + LSE output of the fused-tile kernel (fa_v1_forward_ex)."""
+    Q, K, V = uniform_qkv(B, H, L, d, dtype)
+    f = lambda x: x.float().cpu().numpy().reshape(-1, L, d)
+    q, k, v = f(Q), f(K), f(V)
+    for causal in (False, True):
+        O, lse = ops.flash_attention_v1_ex(Q, K, V, causal=causal, return_lse=True, sync=True)
+        assert not torch.isnan(O).any() and not torch.isnan(lse).any()
+        for h in range(B * H):
+            ref_o, ref_lse = reference.naive_attention_ex_f64(q[h], k[h], v[h], causal=causal)
+            got = O.float().cpu().numpy().reshape(-1, L, d)[h].astype(np.float64)
+            scale = max(1.0, np.abs(ref_o).max() * 2)          # early causal rows are O(1): allow their storage rounding
+            assert np.abs(got - ref_o).max() <= TOL[dtype] * scale
+            assert np.abs(lse.cpu().numpy().reshape(-1, L)[h] - ref_lse).max() <= 2e-3
+        if not causal:
+            assert torch.equal(O, ops.flash_attention_v1(Q, K, V, sync=True))   # same kernel, extras off
+    O = ops.flash_attention_v1_ex(Q, K, V, causal=True, sync=True)
+    # row 0 attends to key 0 only: O[0] = V[0] (tf32 truncates V's mantissa to 10 bits, 16-bit storage is exact)
+    assert (O[:, :, 0].float() - V[:, :, 0].float()).abs().max().item() <= (1e-3 if dtype == torch.float32 else 1e-6)
+
+
+def test_causal_rejects_large_head_dim(ops):
+    from exploring_flash_attention_b200 import FlashAttentionError
+    Q, K, V = uniform_qkv(1, 1, 128, 256, torch.bfloat16)
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_v1_ex(Q, K, V, causal=True)

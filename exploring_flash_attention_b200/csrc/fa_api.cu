@@ -126,7 +126,6 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = o_accum;
   p.lse_accum = lse_accum;
-  p.o_ptr = O;
   p.lse_out = SPLIT ? nullptr : lse_out;
   p.causal = SPLIT ? 0 : causal;
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
@@ -181,7 +180,6 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o_accum = nullptr;
   p.lse_accum = nullptr;
-  p.o_ptr = O;
   p.lse_out = nullptr;
   p.causal = 0;
   auto kern = fa::fa_tiled_d_kernel<D, DT>;

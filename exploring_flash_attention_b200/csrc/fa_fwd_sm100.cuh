@@ -47,14 +47,12 @@ struct FwdParams {
   float scale;       // 1/sqrt(d)
   float* o_accum;    // [n_splits][BH][L][D] fp32, each split normalised by its own l   (SPLIT only)
   float* lse_accum;  // [n_splits][BH][L]    fp32, m/sqrt(d) + ln(l)                     (SPLIT only)
-  void* o_ptr;       // O [BH][L][D] in the storage dtype                                (non-SPLIT)
   float* lse_out;    // optional [BH][L] fp32: log-sum-exp of the scaled scores of each row      (non-SPLIT, may be null)
   int causal;        // != 0: query row r attends to keys 0..r only                            (non-SPLIT)
 };
 
-#ifndef FA_DIRECT_STORE
-#define FA_DIRECT_STORE 0  // 0: O staged in smem + TMA store (ships).  1: registers -> global, frees 32 KB for a 5th K/V
-#endif                     //    ring stage, but the 16-byte row-strided stores cost 11 % at L=1024 for +1 % at L=16384
+// (Tried and dropped: O rows straight from registers to global to buy a 5th K/V ring stage — the row-strided 16-byte
+//  stores cost 11 % at L=1024 for +1 % at L=16384.)
 
 template <int D, int DT>
 struct FwdTraits {
@@ -73,8 +71,8 @@ struct FwdTraits {
   static constexpr int KPR = SWB / 32;             // MMA K-steps per block row
   static constexpr int TILE_BYTES = NBLK * BLK_BYTES;
   static constexpr int UK = 32 / ES;               // MMA K: 16 (16-bit) / 8 (tf32)
-  static constexpr int NS = (TILE_BYTES >= 32768) ? (FA_DIRECT_STORE ? 5 : 4) : 8;  // K/V ring depth
-  static constexpr int STAGING_BYTES = FA_DIRECT_STORE ? 0 : 2 * BLK_BYTES;
+  static constexpr int NS = (TILE_BYTES >= 32768) ? 4 : 8;  // K/V ring depth
+  static constexpr int STAGING_BYTES = 2 * BLK_BYTES;      // one output staging block per softmax warpgroup
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S = 0, TM_O = 256;
   static_assert(256 + 2 * D <= 512, "S and O accumulators must fit TMEM");
@@ -201,7 +199,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      if (!SPLIT && !FA_DIRECT_STORE) tma_prefetch_desc(&tmO);
+      if (!SPLIT) tma_prefetch_desc(&tmO);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, T::TMEM_COLS);
@@ -523,35 +521,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               *reinterpret_cast<float4*>(dst + cc * 32 + x) = v;
             }
         }
-      } else if (FA_DIRECT_STORE) {
-        // Each thread owns one output row: D*ES contiguous bytes written as 16-byte vectors straight from registers.
-        // (A staged TMA store costs 32 KB of smem = one K/V ring stage; the ring stage is worth more at long L.)
-        if (row_g < p.L) {
-          uint8_t* dst = reinterpret_cast<uint8_t*>(p.o_ptr) + (size_t(c.bh) * p.L + row_g) * (size_t(D) * T::ES);
-#pragma unroll
-          for (int u = 0; u < D * T::ES / 16; ++u) {
-            uint4 v;
-            if constexpr (DT == DT_F32) {
-              const int e = u * 4;
-              v.x = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 0]) * inv_l);
-              v.y = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 1]) * inv_l);
-              v.z = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 2]) * inv_l);
-              v.w = __float_as_uint(__uint_as_float(o[e / 32][e % 32 + 3]) * inv_l);
-            } else {
-              const int e = u * 8;
-              auto pk2 = [&](int ee) {
-                const float a0 = __uint_as_float(o[ee / 32][ee % 32]) * inv_l;
-                const float a1 = __uint_as_float(o[ee / 32][ee % 32 + 1]) * inv_l;
-                return (DT == DT_BF16) ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
-              };
-              v.x = pk2(e + 0);
-              v.y = pk2(e + 2);
-              v.z = pk2(e + 4);
-              v.w = pk2(e + 6);
-            }
-            *reinterpret_cast<uint4*>(dst + u * 16) = v;
-          }
-        }
       } else {
         // One 128-byte column block at a time through this warpgroup's staging block (same 128B swizzle), TMA store.
 #pragma unroll
@@ -592,7 +561,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
     }
-    if (!SPLIT && !FA_DIRECT_STORE && storer) tma_store_wait_read_all();  // smem must outlive the last store's read
+    if (!SPLIT && storer) tma_store_wait_read_all();  // smem must outlive the last store's read
   }
 
   tc_fence_before();

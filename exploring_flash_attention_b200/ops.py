@@ -29,6 +29,21 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device_of(fn):
+    """The C ABI launches on the CURRENT device and stream: make the tensors' device current for the call."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+@_on_device_of
 def flash_attention_v1(Q, K, V, O=None, sync: bool = False):
     """O = softmax(Q K^T / sqrt(d)) V for [B,H,L,d] tensors (fused-tile kernel, d <= 128)."""
     Q, K, V = _prep(Q, K, V)
@@ -43,6 +58,7 @@ def flash_attention_v1(Q, K, V, O=None, sync: bool = False):
     return O
 
 
+@_on_device_of
 def flash_attention_v1_ex(Q, K, V, O=None, causal: bool = False, return_lse: bool = False, sync: bool = False):
     """Fused-tile kernel with the extras the reference lists as future work: causal masking and the per-row
     log-sum-exp (natural log of sum_j exp(q.k_j/sqrt(d))). Returns O, or (O, LSE [B,H,L] fp32)."""
@@ -60,6 +76,7 @@ def flash_attention_v1_ex(Q, K, V, O=None, causal: bool = False, return_lse: boo
     return (O, lse) if return_lse else O
 
 
+@_on_device_of
 def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: int = 32, sync: bool = False):
     """Tiled-d variant (head dims up to 512); d_tile_* are validated streaming hints."""
     Q, K, V = _prep(Q, K, V)
@@ -87,6 +104,7 @@ def v2_workspace(B, H, L, d, kv_per_split, device):
             torch.empty((S, B * H, L), dtype=torch.float32, device=device))
 
 
+@_on_device_of
 def flash_attention_v2_splitkv(Q, K, V, kv_per_split: int, Oaccum=None, LSEaccum=None):
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
@@ -98,6 +116,7 @@ def flash_attention_v2_splitkv(Q, K, V, kv_per_split: int, Oaccum=None, LSEaccum
     return Oaccum, LSEaccum
 
 
+@_on_device_of
 def flash_attention_v2_combine(Oaccum, LSEaccum, out_dtype, shape, O=None):
     B, H, L, d = shape
     S = Oaccum.shape[0]
@@ -109,6 +128,7 @@ def flash_attention_v2_combine(Oaccum, LSEaccum, out_dtype, shape, O=None):
     return O
 
 
+@_on_device_of
 def flash_attention_v2(Q, K, V, kv_per_split: int, O=None, workspace=None, sync: bool = False):
     """Split-KV forward + combine. `workspace` = (Oaccum, LSEaccum) from v2_workspace(), reused across calls."""
     Q, K, V = _prep(Q, K, V)

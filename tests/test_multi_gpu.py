@@ -53,3 +53,21 @@ def test_two_gpu_head_sharding_nccl_gather():
     ref = reference.naive_attention_batched_f64(Q, K, V)
     assert full.shape == ref.shape
     assert np.abs(full - ref).max() <= 2e-3
+
+
+def test_tensors_on_a_non_current_device():
+    """The C ABI launches on the current device; ops must switch to the tensors' device (cuda:1 while cuda:0 is current)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from exploring_flash_attention_b200 import ops
+    from oracle import reference
+    torch.cuda.set_device(0)
+    g = torch.Generator().manual_seed(5)
+    Q, K, V = ((torch.rand((1, 2, 300, 64), generator=g) * 2 - 1).bfloat16().to("cuda:1") for _ in range(3))
+    O = ops.flash_attention_v1(Q, K, V, sync=True)
+    O2 = ops.flash_attention_v2(Q, K, V, 128, sync=True)
+    torch.cuda.synchronize(1)
+    assert O.device.index == 1 and torch.cuda.current_device() == 0
+    ref = reference.naive_attention_batched_f64(*(x.float().cpu().numpy() for x in (Q, K, V)))
+    assert np.abs(O.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
+    assert np.abs(O2.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3

@@ -332,3 +332,36 @@ def test_causal_rejects_large_head_dim(ops):
     Q, K, V = uniform_qkv(1, 1, 128, 256, torch.bfloat16)
     with pytest.raises(FlashAttentionError):
         ops.flash_attention_v1_ex(Q, K, V, causal=True)
+
+
+def test_v2_reference_signature_kernels_driver_loop(ops, golden):
+    """The reference's two-kernel driver loop (flash_attention_v2/numpy_gpu_like.py:378-402) written against our
+    reference-signature partial_attention_kernel / reduction_kernel, on the golden V2 case (L=52 ragged, d=64, fp16)."""
+    from exploring_flash_attention_b200.flash_attention_v2 import partial_attention_kernel, reduction_kernel
+    seed, L, d = SMALL_CASES["v2"]
+    Bq = Bk = 8
+    tiles = 4
+    Q, K, V = qkv(seed, L, d, np.float16)
+    wO, wm, wl = {}, {}, {}
+    nq, nkt = -(-L // Bq), -(-L // Bk)
+    nkb = -(-nkt // tiles)
+    for qt in range(nq):
+        for kb in range(nkb):
+            partial_attention_kernel(Q.flatten(), K.flatten(), V.flatten(), wO, wm, wl, qt, kb, L, d, Bq, Bk, 16, 16,
+                                     kb * tiles, min(kb * tiles + tiles, nkt))
+    O = np.zeros(L * d, dtype=np.float16)
+    for qt in range(nq):
+        reduction_kernel(wO, wm, wl, O, qt, nkb, L, d, Bq)
+    ref64 = reference.naive_attention_f64(Q, K, V)
+    assert np.abs(O.reshape(L, d).astype(np.float64) - ref64).max() <= 4e-3
+    assert np.abs(O.reshape(L, d).astype(np.float64) - golden["v2_f16_O"].astype(np.float64)).max() <= 6e-3
+    # the GPU reduction also merges the REFERENCE's own (un-normalised O, m, l) workspace triples
+    from oracle import tiled
+    rO, rm, rl = {}, {}, {}
+    Od = np.zeros(L * d, dtype=np.float64)
+    Q64, K64, V64 = (x.astype(np.float64) for x in (Q, K, V))
+    tiled.flash_attention_tiled_v2(Q64.flatten(), K64.flatten(), V64.flatten(), Od, rO, rm, rl, L, d, Bq, Bk, 16, 16, tiles)
+    O2 = np.zeros(L * d, dtype=np.float64)
+    for qt in range(nq):
+        reduction_kernel(rO, rm, rl, O2, qt, nkb, L, d, Bq)
+    assert np.abs(O2 - Od).max() <= 1e-5

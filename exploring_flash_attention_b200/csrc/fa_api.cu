@@ -198,7 +198,9 @@ int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int B
   if (d == 512 && dtype == fa::DT_BF16) return launch_tiled_d<512, fa::DT_BF16>(Q, K, V, O, BH, L, s);
   if (d == 256 && dtype == fa::DT_F16) return launch_tiled_d<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
   if (d == 512 && dtype == fa::DT_F16) return launch_tiled_d<512, fa::DT_F16>(Q, K, V, O, BH, L, s);
-  return fail(FA_ERR_UNSUPPORTED_D, "tiled-d kernel serves d in {256,512} for bf16/fp16; got d=" + std::to_string(d) +
+  if (d == 128 && dtype == fa::DT_F32) return launch_tiled_d<128, fa::DT_F32>(Q, K, V, O, BH, L, s);
+  if (d == 256 && dtype == fa::DT_F32) return launch_tiled_d<256, fa::DT_F32>(Q, K, V, O, BH, L, s);
+  return fail(FA_ERR_UNSUPPORTED_D, "tiled-d kernel serves d in {256,512} for bf16/fp16 and d in {128,256} for fp32; got d=" + std::to_string(d) +
                                         " dtype=" + std::to_string(dtype));
 }
 
@@ -250,7 +252,8 @@ int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, i
                   void* stream) {
   int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
   if (rc != FA_OK) return rc;
-  if (d > 128) return fa_v1_tiled_d_forward(Q, K, V, O, B, H, L, d, d >= 64 ? 64 : d, d >= 64 ? 64 : d, dtype, stream);
+  if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
+    return fa_v1_tiled_d_forward(Q, K, V, O, B, H, L, d, d >= 64 ? 64 : d, d >= 64 ? 64 : d, dtype, stream);
   return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
@@ -272,7 +275,8 @@ int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, 
   if (d_tile_qk <= 0 || d_tile_v <= 0 || d % d_tile_qk != 0 || d % d_tile_v != 0)
     return fail(FA_ERR_SHAPE, "d_tile_qk and d_tile_v must be positive divisors of d");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (d <= 128) return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
+  if (d <= 128 && !(dtype == FA_DTYPE_F32 && d > 64))
+    return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
   return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, s);
 }
 

@@ -1,4 +1,6 @@
-// fa_tiled_d_sm100.cuh — K2: tiled-d flash-attention forward for head dims 256 and 512 (16-bit storage).
+// fa_tiled_d_sm100.cuh — K2: tiled-d flash-attention forward for head-dim rows of 512 or 1024 bytes: d = 256, 512 in
+// 16-bit storage, d = 128, 256 in fp32 storage (tf32 tensor-core products) — the reference's tiled-d default D=128 in its
+// USE_FP64 mode maps onto the latter.
 //
 // Replaces, for d > 128 (same semantics, [B,H,L,d] contiguous, dense, scale 1/sqrt(d)):
 //   flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:230-309      flash_attention_kernel (scalar, O in fp32 regs)
@@ -28,14 +30,17 @@ namespace fa {
 
 template <int D, int DT>
 struct TiledDTraits {
-  static_assert(DT != DT_F32, "tiled-d kernel is 16-bit storage only");
-  static_assert(D == 256 || D == 512, "tiled-d kernel serves d = 256, 512");
-  static constexpr uint32_t FMT = (DT == DT_BF16) ? FMT_BF16 : FMT_F16;
+  static constexpr int ES = (DT == DT_F32) ? 4 : 2;
+  static_assert(D * ES >= 512 && D * ES <= 1024 && (D == 128 || D == 256 || D == 512),
+                "tiled-d kernel serves d = 256, 512 (16-bit) and d = 128, 256 (fp32 storage / tf32 products)");
+  static constexpr uint32_t FMT = (DT == DT_F32) ? FMT_TF32 : (DT == DT_BF16 ? FMT_BF16 : FMT_F16);
+  static constexpr uint32_t KIND = (DT == DT_F32) ? KIND_TF32 : KIND_F16;
+  static constexpr int UK = 32 / ES;                    // MMA K: 16 (16-bit) / 8 (tf32)
   static constexpr int BM = 128, BN = 128;
-  static constexpr int CH = 64;                         // head-dim chunk (elements) = one 128-byte swizzle row
+  static constexpr int CH = 128 / ES;                   // head-dim chunk (elements) = one 128-byte swizzle row
   static constexpr int BLK_BYTES = 128 * 128;           // one chunk block: 128 rows x 128 B
   static constexpr int NKC = D / CH;                    // K (and Q) chunks per tile
-  static constexpr int DV = 256;                        // output columns owned by one CTA
+  static constexpr int DV = D < 256 ? D : 256;          // output columns owned by one CTA
   static constexpr int NVC = DV / CH;                   // V chunks per tile
   static constexpr int NSLAB = D / DV;
   static constexpr int Q_BYTES = NKC * BLK_BYTES;
@@ -132,7 +137,9 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       constexpr uint32_t idesc_qk = make_idesc(T::FMT, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(T::FMT, BM, CH, 0, 1);
       constexpr uint64_t hiK = make_smem_desc_hi(16, 1024, SWZ_128B);
-      constexpr uint64_t hiV = make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
+      // 32-bit MN-major operands exist only in the 128B-swizzle / 32B-atom layout (4-key atoms 512 B apart)
+      constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
+                                              : make_smem_desc_hi(BLK_BYTES, 1024, SWZ_128B);
       const uint32_t sQ_addr = smem_u32(sQ), ring_addr = smem_u32(sRing);
       int it = 0;
       auto qk = [&](int b) {  // S[b] = Q K^T, accumulated over the d chunks as they land
@@ -141,8 +148,8 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_wait(&full[stage], (it / NS) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < CH / 16; ++k)
-            umma_ss<KIND_F16>(tmem_base + T::TM_S + b * BN, make_smem_desc(sQ_addr + c * BLK_BYTES + k * 32, hiK),
+          for (int k = 0; k < CH / T::UK; ++k)
+            umma_ss<T::KIND>(tmem_base + T::TM_S + b * BN, make_smem_desc(sQ_addr + c * BLK_BYTES + k * 32, hiK),
                               make_smem_desc(ring_addr + stage * BLK_BYTES + k * 32, hiK), idesc_qk, (c | k) ? 1u : 0u);
           tc_commit(&empty[stage]);
           ++it;
@@ -155,9 +162,9 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_wait(&full[stage], (it / NS) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk)
-            umma_ts<KIND_F16>(tmem_base + T::TM_O + v * CH, tmem_base + T::TM_S + b * BN + kk * 8,
-                              make_smem_desc(ring_addr + stage * BLK_BYTES + kk * 16 * 128, hiV), idesc_pv,
+          for (int kk = 0; kk < BN / T::UK; ++kk)
+            umma_ts<T::KIND>(tmem_base + T::TM_O + v * CH, tmem_base + T::TM_S + b * BN + kk * 8,
+                              make_smem_desc(ring_addr + stage * BLK_BYTES + kk * T::UK * 128, hiV), idesc_pv,
                               (acc | (kk > 0)) ? 1u : 0u);
           tc_commit(&empty[stage]);
           ++it;
@@ -247,16 +254,21 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         s[3][x] = __float_as_uint(p3);
       }
       l += (l0 + l1) + (l2 + l3);
-      uint32_t pk[2][32];
+      if constexpr (DT == DT_F32) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c) tmem_st32(tS + c * 32, s[c]);   // fp32 P in place over S (tf32 A operand)
+      } else {
+        uint32_t pk[2][32];
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          const float a = __uint_as_float(s[c][2 * x]), b = __uint_as_float(s[c][2 * x + 1]);
-          pk[c >> 1][(c & 1) * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
-        }
-      tmem_st32(tS, pk[0]);
-      tmem_st32(tS + 32, pk[1]);
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const float a = __uint_as_float(s[c][2 * x]), b = __uint_as_float(s[c][2 * x + 1]);
+            pk[c >> 1][(c & 1) * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+          }
+        tmem_st32(tS, pk[0]);
+        tmem_st32(tS + 32, pk[1]);
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[j & 1]);
@@ -274,18 +286,26 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint32_t o[32];
       tmem_ld32(tO + c * 32, o);
       tc_wait_ld();
+      constexpr int CPC = 32 * T::ES / 16;  // 16-byte chunks produced by 32 columns: 4 (16-bit) / 8 (fp32)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // 4 x 16-byte chunks per 32 columns
-        auto pk2 = [&](int e) {
-          const float a = __uint_as_float(o[e]) * inv_l, b = __uint_as_float(o[e + 1]) * inv_l;
-          return (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
-        };
+      for (int u = 0; u < CPC; ++u) {
         uint4 v;
-        v.x = pk2(8 * u + 0);
-        v.y = pk2(8 * u + 2);
-        v.z = pk2(8 * u + 4);
-        v.w = pk2(8 * u + 6);
-        const int q = c * 4 + u;  // 16-byte chunk index within the 512-byte slab row
+        if constexpr (DT == DT_F32) {
+          v.x = __float_as_uint(__uint_as_float(o[4 * u + 0]) * inv_l);
+          v.y = __float_as_uint(__uint_as_float(o[4 * u + 1]) * inv_l);
+          v.z = __float_as_uint(__uint_as_float(o[4 * u + 2]) * inv_l);
+          v.w = __float_as_uint(__uint_as_float(o[4 * u + 3]) * inv_l);
+        } else {
+          auto pk2 = [&](int e) {
+            const float a = __uint_as_float(o[e]) * inv_l, b = __uint_as_float(o[e + 1]) * inv_l;
+            return (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+          };
+          v.x = pk2(8 * u + 0);
+          v.y = pk2(8 * u + 2);
+          v.z = pk2(8 * u + 4);
+          v.w = pk2(8 * u + 6);
+        }
+        const int q = c * CPC + u;  // 16-byte chunk index within the slab row
         uint8_t* dst = sQ + (q >> 3) * BLK_BYTES + row * 128 + (((q & 7) ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(dst) = v;
       }
@@ -306,6 +326,8 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 // Host-side dispatch lives in fa_api.cu (tensor maps); this helper only reports the supported set.
-inline bool tiled_d_supported(int d, int dtype) { return (d == 256 || d == 512) && (dtype == DT_BF16 || dtype == DT_F16); }
+inline bool tiled_d_supported(int d, int dtype) {
+  return dtype == DT_F32 ? (d == 128 || d == 256) : (d == 256 || d == 512);
+}
 
 }  // namespace fa

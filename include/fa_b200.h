@@ -48,7 +48,8 @@ int fa_device_sm_count(void);
  * Replaces  void flash_attention_v1(const DATA_TYPE* Q, K, V, DATA_TYPE* O, int B, int H, int L, int d_runtime)
  *           flash_attention_v1/CUDA/flash_attention_v1.h:251-293  and  flash_attention_v1_opt1(...)
  *           flash_attention_v1/CUDA/flash_attention_v1_opt1.h:354-396.
- * d in {32,64,128} for 16-bit dtypes, {32,64} for FA_DTYPE_F32; d in {256,512} (16-bit) is routed to the tiled-d kernel. */
+ * d in {32,64,128} for 16-bit dtypes, {32,64} for FA_DTYPE_F32; d in {256,512} (16-bit) and {128,256} (fp32) are
+ * routed to the tiled-d kernel. */
 int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int dtype,
                   void* stream /* cudaStream_t */);
 

@@ -41,6 +41,7 @@ CASES = [
     ("td_d512", "v1", 1, 2, 512, 512, "bf16", 0),
     ("td_d256_big", "v1", 4, 8, 4096, 256, "bf16", 0),
     ("C5_full", "v1", 16, 8, 4096, 512, "bf16", 0),
+    ("C2_tf32", "v1", 32, 8, 1024, 128, "f32", 0),
 ]
 
 

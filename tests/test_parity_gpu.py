@@ -72,6 +72,9 @@ def test_v1_matches_oracle(ops, B, H, L, d, dtype):
     (1, 2, 256, 256, torch.bfloat16), (1, 2, 384, 512, torch.bfloat16), (1, 1, 512, 512, torch.float16),
     (1, 2, 333, 512, torch.bfloat16), (1, 1, 100, 256, torch.float16), (2, 1, 129, 512, torch.bfloat16),
     (1, 1, 1, 512, torch.bfloat16),
+    # fp32 storage / tf32 products through the same kernel: the reference tiled-d default D=128 in its USE_FP64 mode
+    (2, 2, 512, 128, torch.float32), (1, 2, 333, 128, torch.float32), (1, 2, 300, 256, torch.float32),
+    (1, 1, 100, 128, torch.float32),
 ])
 def test_tiled_d_large_head_dims_match_oracle(ops, B, H, L, d, dtype):
     """K2: d = 256 / 512 (TMEM holds one 256-wide O slab per CTA); d_tile hints are validated like the reference."""

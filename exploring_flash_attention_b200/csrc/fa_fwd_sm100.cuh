@@ -21,6 +21,7 @@
 //     warp  9    tcgen05.mma issuer (one elected lane)      (warps 10-11 idle: setmaxnreg works per warpgroup)
 //   TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P overwrites S in place
 //     (packed 16-bit pairs for bf16/fp16, fp32 words for tf32) and feeds the PV MMA as the TMEM A operand.
+//     16-bit d <= 64 (SEP_P): P0/P1 get their own 64 columns after O, which lets QK_i(j+1) run under softmax_i(j).
 //   smem: Q 2 tiles + NS-stage K/V ring + one output staging block per warpgroup, all swizzled [128 rows x 128 B]
 //     blocks moved by TMA (64-byte rows / 64B swizzle when the head-dim row is only 64 bytes: 16-bit d = 32).
 //   The two Q tiles ping-pong on the tensor pipe: while warpgroup i runs softmax on S_i the MMA warp issues PV/QK for
@@ -76,7 +77,12 @@ struct FwdTraits {
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S = 0, TM_O = 256;
   static_assert(256 + 2 * D <= 512, "S and O accumulators must fit TMEM");
-  static constexpr int NUM_BARS = 2 + 2 + 2 * NS + 2 + 4 + 2 + 2;
+  // 16-bit P_i is 64 TMEM columns.  When they fit next to S and O (d <= 64) P gets its own columns instead of aliasing
+  // S_i, so QK_i(j+1) can be issued as soon as S_i(j) is in registers and runs under softmax_i(j) instead of after it.
+  static constexpr bool SEP_P = (DT != DT_F32) && (256 + 2 * D + 128 <= 512);
+  static constexpr int TM_P = SEP_P ? 256 + 2 * D : TM_S;
+  static constexpr int P_STRIDE = SEP_P ? 64 : BN;   // columns between P_0 and P_1
+  static constexpr int NUM_BARS = 2 + 2 + 2 * NS + 2 + 4 + 2 + 2 + 4;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 + NS) * TILE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16;
   static constexpr int THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle}
 };
@@ -173,7 +179,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* p_full = s_full + 2;        // [2][2] softmax (128 arrivals) -> MMA: key-half h of P_i(j) in TMEM, O_i rescaled
   uint64_t* o_done = p_full + 4;        // [2]  MMA -> softmax: last PV_i of this item retired
   uint64_t* o_free = o_done + 2;        // [2]  softmax (128 arrivals) -> MMA: O_i read out, next item may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_free = o_free + 2;        // [2]  SEP_P: softmax (128 arrivals) -> MMA: S_i(j) is in registers
+  uint64_t* pv_done = s_free + 2;       // [2]  SEP_P: MMA (commit) -> softmax: PV_i(j) retired (P_i and O_i quiescent)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,6 +195,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
       mbar_init(&o_free[i], 128);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -269,7 +279,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const uint32_t b_base = sKV_addr + stage * TILE_BYTES;
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
-            umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_S + i * BN + kk * 8,
+            umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_P + i * T::P_STRIDE + kk * (UK * T::ES / 4),
                           make_smem_desc(b_base + kk * UK * T::SWB, hiV), idesc_pv, (acc | (kk > 0)) ? 1u : 0u);
           }
         };
@@ -277,6 +287,68 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         int tt = 0;            // K/V tiles consumed so far (ring position), across items
         int nt[2] = {0, 0};    // KV tiles processed for Q tile i (phase of s_full / p_full), across items
         int ni[2] = {0, 0};    // items processed for Q tile i (phase of q_full / o_done / o_free)
+        if constexpr (T::SEP_P) {
+          // P_i has its own TMEM columns: per KV step issue both QK(j+1) first (each as soon as its S_i(j) has been
+          // read out), then both PV(j) as their P halves arrive.  S_i(j+1) is then ready before softmax_i(j) ends.
+          int nqk[2] = {0, 0};  // QK_i issued so far (phase of s_free), across items
+          for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const ItemCoord c = decode_item<SPLIT>(item, p);
+            const int t0 = tt;
+            mbar_wait(&kv_full[t0 % NS], (t0 / NS) & 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i >= c.n_q) continue;
+              mbar_wait(&q_full[i], ni[i] & 1);
+              if (nqk[i] > 0) mbar_wait(&s_free[i], (nqk[i] - 1) & 1);
+              tc_fence_after();
+              qk(i, t0 % NS);
+              tc_commit(&s_full[i]);
+              ++nqk[i];
+              if (c.nt[i] == 1) tc_commit(&q_empty[i]);
+            }
+            tc_commit(&kv_empty[t0 % NS]);
+            for (int j = 0; j < c.n_tiles; ++j) {
+              const int tv = t0 + 2 * j + 1, tk = t0 + 2 * j + 2;
+              if (j + 1 < c.n_tiles) {
+                mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  if (i >= c.n_q || j + 1 >= c.nt[i]) continue;
+                  mbar_wait(&s_free[i], (nqk[i] - 1) & 1);
+                  tc_fence_after();
+                  qk(i, tk % NS);
+                  tc_commit(&s_full[i]);
+                  ++nqk[i];
+                  if (j + 2 == c.nt[i]) tc_commit(&q_empty[i]);
+                }
+                tc_commit(&kv_empty[tk % NS]);
+              }
+              mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                if (i >= c.n_q || j >= c.nt[i]) continue;
+                if (j == 0 && ni[i] > 0) mbar_wait(&o_free[i], (ni[i] - 1) & 1);
+                mbar_wait(&p_full[2 * i], nt[i] & 1);
+                tc_fence_after();
+                if (FA_P_HALVES) {
+                  pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+                  mbar_wait(&p_full[2 * i + 1], nt[i] & 1);
+                  tc_fence_after();
+                  pv(i, tv % NS, 1u, KT / 2, KT);
+                } else {
+                  pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
+                }
+                ++nt[i];
+                tc_commit(&pv_done[i]);
+                if (j + 1 == c.nt[i]) tc_commit(&o_done[i]);
+              }
+              tc_commit(&kv_empty[tv % NS]);
+            }
+            tt = t0 + 2 * c.n_tiles;
+            ++ni[0];
+            if (c.n_q > 1) ++ni[1];
+          }
+        } else
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const ItemCoord c = decode_item<SPLIT>(item, p);
           const int t0 = tt;   // ring index of K_0 of this item
@@ -343,6 +415,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
     const uint32_t tS = t_lane + T::TM_S + i * BN;
     const uint32_t tO = t_lane + T::TM_O + i * D;
+    const uint32_t tP = t_lane + T::TM_P + i * T::P_STRIDE;  // 16-bit P_i (aliases S_i unless SEP_P)
     uint8_t* sO = sOut + i * BLK_BYTES;
     const uint32_t sO_addr = smem_u32(sO);
     const bool storer = ((warp & 3) == 0) && (lane == 0);
@@ -364,6 +437,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s[cc]);
         tc_wait_ld();
+        if constexpr (T::SEP_P) {
+          tc_fence_before();
+          mbar_arrive(&s_free[i]);  // S_i(j) is in registers: QK_i(j+1) may overwrite it while this tile's exp runs
+        }
 
         // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
         // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
@@ -396,6 +473,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           asm volatile("" ::: "memory");  // keep this a real branch
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if constexpr (T::SEP_P) {
+          // QK_i(j) was issued ahead of PV_i(j-1) here, so s_full no longer implies that PV retired: wait for it before
+          // O_i is rescaled or P_i overwritten (it was issued a whole tile period ago; this does not spin in steady state).
+          if (nt > 0) {
+            mbar_wait(&pv_done[i], (nt - 1) & 1);
+            tc_fence_after();
+          }
+        }
 
         if (j == 0) {
           m_used = mx;
@@ -403,7 +488,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           // Lazy rescale: keep the stale max unless the new one is > 2^8 larger (in exp2 units).
           const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // s_full[i](j) retiring implies PV_i(j-1) retired (same issuing thread, in-order pipe), so O_i is quiescent.
+            // PV_i(j-1) has retired, so O_i is quiescent: without SEP_P s_full[i](j) implies it (same issuing thread,
+            // in-order pipe); with SEP_P the pv_done wait above does.
             const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
             if (need) m_used = mx;
             l *= alpha;
@@ -468,7 +554,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                   const float a = __uint_as_float(s[cc + h][2 * x]), b = __uint_as_float(s[cc + h][2 * x + 1]);
                   pk[h * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
                 }
-              tmem_st32(tS + (cc / 2) * 32, pk);
+              tmem_st32(tP + (cc / 2) * 32, pk);
             }
           }
         };

@@ -42,6 +42,11 @@ CASES = [
     ("td_d256_big", "v1", 4, 8, 4096, 256, "bf16", 0),
     ("C5_full", "v1", 16, 8, 4096, 512, "bf16", 0),
     ("C2_tf32", "v1", 32, 8, 1024, 128, "f32", 0),
+    ("d64_bf16_L1024", "v1", 32, 8, 1024, 64, "bf16", 0),
+    ("d64_bf16_L8192", "v1", 2, 16, 8192, 64, "bf16", 0),
+    ("d32_f16_L8192", "v1", 2, 16, 8192, 32, "f16", 0),
+    ("d64_bf16_causal", "causal", 4, 8, 4096, 64, "bf16", 0),
+    ("d64_bf16_v2", "v2", 2, 8, 4096, 64, "bf16", 1024),
 ]
 
 

@@ -99,15 +99,24 @@ int check_common(const void* Q, const void* K, const void* V, const void* O, int
   return FA_OK;
 }
 
+// Optional arguments of the fused-tile kernel beyond the reference's (Q,K,V,O,B,H,L,d).
+struct FwdExtra {
+  int Lk = 0;                    // keys per head when it differs from the query count (0: same as L)
+  int H = 0;                     // heads per batch entry (needed with kv_lens)
+  const int* kv_lens = nullptr;  // device [B] int32 key-padding lengths
+};
+
 template <int D, int DT, bool SPLIT>
 int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int kv_per_split, int n_splits,
-               float* o_accum, float* lse_accum, cudaStream_t stream, float* lse_out = nullptr, int causal = 0) {
+               float* o_accum, float* lse_accum, cudaStream_t stream, float* lse_out = nullptr, int causal = 0,
+               const FwdExtra& ex = FwdExtra()) {
   using T = fa::FwdTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
+  const int Lk = ex.Lk > 0 ? ex.Lk : L;
   if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, Lk, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, Lk, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
   if (SPLIT) {
     tmO = tmQ;  // unused by the split epilogue
   } else if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) {
@@ -115,8 +124,11 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   }
   fa::FwdParams p;
   p.L = L;
+  p.Lk = Lk;
   p.BH = BH;
-  p.kv_per_split = SPLIT ? kv_per_split : L;
+  p.H = ex.H > 0 ? ex.H : 1;
+  p.kv_lens = SPLIT ? nullptr : ex.kv_lens;
+  p.kv_per_split = SPLIT ? kv_per_split : Lk;
   p.n_splits = SPLIT ? n_splits : 1;
   p.n_qpairs = (L + 255) / 256;
   const long long items = (long long)BH * p.n_splits * p.n_qpairs;
@@ -142,10 +154,11 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
 template <bool SPLIT>
 int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
                  int kv_per_split, int n_splits, float* o_accum, float* lse_accum, cudaStream_t s,
-                 float* lse_out = nullptr, int causal = 0) {
+                 float* lse_out = nullptr, int causal = 0, const FwdExtra& ex = FwdExtra()) {
 #define FA_CASE(DD, DTT)                                                                                         \
   if (d == DD && dtype == DTT)                                                                                   \
-    return launch_fwd<DD, DTT, SPLIT>(Q, K, V, O, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s, lse_out, causal);
+    return launch_fwd<DD, DTT, SPLIT>(Q, K, V, O, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s, lse_out, \
+                                      causal, ex);
   FA_CASE(128, fa::DT_BF16)
   FA_CASE(64, fa::DT_BF16)
   FA_CASE(128, fa::DT_F16)
@@ -265,6 +278,38 @@ int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float
   if (d > 128) return fail(FA_ERR_UNSUPPORTED_D, "LSE output / causal masking are served by the fused-tile kernel only (d <= 128)");
   return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
                              LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0);
+}
+
+int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, float* LSE, const int* kv_lens, int B,
+                         int H, int Lq, int Lk, int d, int dtype, unsigned flags, void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, Lq, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (Lk <= 0) return fail(FA_ERR_SHAPE, "Lk must be positive");
+  if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
+  if ((flags & FA_FLAG_CAUSAL) && Lq != Lk) return fail(FA_ERR_SHAPE, "causal masking needs Lq == Lk");
+  if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
+    return fail(FA_ERR_UNSUPPORTED_D, "key-padding / Lq != Lk are served by the fused-tile kernel only (row of at most 256 bytes)");
+  FwdExtra ex;
+  ex.Lk = Lk;
+  ex.H = H;
+  ex.kv_lens = kv_lens;
+  return dispatch_fwd<false>(Q, K, V, O, B * H, Lq, d, dtype, Lk, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
+                             LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0, ex);
+}
+
+int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opartial, float* LSEpartial, int B, int H,
+                       int Lq, int Lk, int d, int dtype, void* stream) {
+  int rc = check_common(Q, K, V, Opartial, B, H, Lq, d, dtype);
+  if (rc != FA_OK) return rc;
+  if (Lk <= 0) return fail(FA_ERR_SHAPE, "Lk must be positive");
+  if (LSEpartial == nullptr) return fail(FA_ERR_ALIGN, "LSEpartial must be non-null");
+  if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
+    return fail(FA_ERR_UNSUPPORTED_D, "partial attention is served by the fused-tile kernel only (row of at most 256 bytes)");
+  FwdExtra ex;
+  ex.Lk = Lk;
+  ex.H = H;
+  return dispatch_fwd<true>(Q, K, V, nullptr, B * H, Lq, d, dtype, /*kv_per_split=*/Lk, /*n_splits=*/1, Opartial,
+                            LSEpartial, static_cast<cudaStream_t>(stream), nullptr, 0, ex);
 }
 
 int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,

@@ -38,8 +38,11 @@ namespace fa {
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 
 struct FwdParams {
-  int L;             // sequence length (queries == keys)
+  int L;             // query rows per head
+  int Lk;            // keys per head (== L except for partial / context-parallel calls)
   int BH;            // B*H
+  int H;             // heads per batch entry (indexes kv_lens)
+  const int* kv_lens;  // optional [B] int32: batch entry b attends to its first kv_lens[b] keys only (non-SPLIT, may be null)
   int kv_per_split;  // keys handled by one split (== L when SPLIT is false)
   int n_splits;
   int n_qpairs;      // ceil(L / 256)
@@ -143,8 +146,10 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   c.split = SPLIT ? rest % p.n_splits : 0;
   c.bh = SPLIT ? rest / p.n_splits : rest;
   c.q_row0 = qp * 256;
+  int kv_len = p.Lk;
+  if (!SPLIT && p.kv_lens != nullptr) kv_len = max(1, min(p.Lk, __ldg(p.kv_lens + c.bh / p.H)));  // key-padding mask
   c.kv_begin = SPLIT ? c.split * p.kv_per_split : 0;
-  c.kv_end = SPLIT ? min(p.L, c.kv_begin + p.kv_per_split) : p.L;
+  c.kv_end = SPLIT ? min(kv_len, c.kv_begin + p.kv_per_split) : kv_len;
   c.n_tiles = (c.kv_end - c.kv_begin + 127) / 128;
   c.n_q = (p.L - c.q_row0 > 128) ? 2 : 1;
   c.nt[0] = c.nt[1] = c.n_tiles;

@@ -76,6 +76,65 @@ def flash_attention_v1_ex(Q, K, V, O=None, causal: bool = False, return_lse: boo
     return (O, lse) if return_lse else O
 
 
+def _prep_rect(Q, K, V):
+    """Like _prep, but K/V may hold a different number of rows than Q ([B,H,Lq,d] vs [B,H,Lk,d])."""
+    if not (Q.is_cuda and K.is_cuda and V.is_cuda):
+        raise RuntimeError("flash-attention B200 path needs CUDA tensors: there is no CPU fallback")
+    if Q.dtype not in _DTYPES:
+        raise _lib.FlashAttentionError(-2, f"unsupported dtype {Q.dtype}")
+    if not (Q.dtype == K.dtype == V.dtype):
+        raise _lib.FlashAttentionError(-2, "Q, K, V must share a dtype")
+    if Q.dim() != 4 or K.dim() != 4 or K.shape != V.shape or Q.shape[:2] != K.shape[:2] or Q.shape[3] != K.shape[3]:
+        raise _lib.FlashAttentionError(-1, "Q must be [B,H,Lq,d] and K, V [B,H,Lk,d]")
+    return Q.contiguous(), K.contiguous(), V.contiguous()
+
+
+@_on_device_of
+def flash_attention_varlen(Q, K, V, kv_lens=None, O=None, causal: bool = False, return_lse: bool = False,
+                           sync: bool = False):
+    """Fused-tile kernel with a key-padding mask and/or Lq != Lk ("dynamic sequence lengths", which the reference
+    lists as future work, flash_attention_v1/README_v1.md:169).  kv_lens: int32 [B] on the device — batch entry b
+    attends to its first kv_lens[b] keys (clamped to [1, Lk])."""
+    Q, K, V = _prep_rect(Q, K, V)
+    B, H, Lq, d = Q.shape
+    Lk = K.shape[2]
+    if O is None:
+        O = torch.empty_like(Q)
+    if kv_lens is not None:
+        if kv_lens.dtype != torch.int32 or kv_lens.numel() != B or kv_lens.device != Q.device:
+            raise _lib.FlashAttentionError(-1, "kv_lens must be an int32 tensor of B entries on Q's device")
+        kv_lens = kv_lens.contiguous()
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=Q.device) if return_lse else None
+    lib = _lib.load()
+    _lib.check(lib.fa_v1_forward_varlen(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                        lse.data_ptr() if return_lse else None,
+                                        kv_lens.data_ptr() if kv_lens is not None else None,
+                                        B, H, Lq, Lk, d, _DTYPES[Q.dtype], 1 if causal else 0, _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return (O, lse) if return_lse else O
+
+
+@_on_device_of
+def flash_attention_partial(Q, K, V, Opartial=None, LSEpartial=None):
+    """One un-merged attention partial: Q [B,H,Lq,d] against one key/value shard [B,H,Lk,d].
+    Returns (Opartial [B*H,Lq,d] fp32 normalised by the shard's own row sums, LSEpartial [B*H,Lq] fp32);
+    partials stacked on a leading axis are flash_attention_v2_combine's input."""
+    Q, K, V = _prep_rect(Q, K, V)
+    B, H, Lq, d = Q.shape
+    Lk = K.shape[2]
+    if Opartial is None:
+        Opartial = torch.empty((B * H, Lq, d), dtype=torch.float32, device=Q.device)
+    if LSEpartial is None:
+        LSEpartial = torch.empty((B * H, Lq), dtype=torch.float32, device=Q.device)
+    if not (Opartial.is_contiguous() and LSEpartial.is_contiguous()):
+        raise _lib.FlashAttentionError(-3, "Opartial / LSEpartial must be contiguous")
+    lib = _lib.load()
+    _lib.check(lib.fa_partial_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), Opartial.data_ptr(),
+                                      LSEpartial.data_ptr(), B, H, Lq, Lk, d, _DTYPES[Q.dtype], _stream()))
+    return Opartial, LSEpartial
+
+
 @_on_device_of
 def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: int = 32, sync: bool = False):
     """Tiled-d variant (head dims up to 512); d_tile_* are validated streaming hints."""

@@ -62,6 +62,22 @@ int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, i
 int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int L, int d,
                      int dtype, unsigned flags, void* stream);
 
+/* Key-padding mask and rectangular attention ("dynamic sequence lengths"):
+ *   Q, O [B,H,Lq,d];  K, V [B,H,Lk,d];
+ *   kv_lens optional device int32[B]: every head of batch entry b attends to its first kv_lens[b] keys only
+ *           (values are clamped to [1, Lk]; NULL = all Lk keys).  KV tiles past the length are never loaded.
+ *   FA_FLAG_CAUSAL needs Lq == Lk.  Rows of at most 256 bytes (the fused-tile kernel). */
+int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, float* LSE, const int* kv_lens, int B,
+                         int H, int Lq, int Lk, int d, int dtype, unsigned flags, void* stream);
+
+/* One un-merged partial of attention (the multi-GPU generalisation of V2's split-KV,
+ * flash_attention_v2/README.md:5-21): queries [B,H,Lq,d] against ONE shard of keys/values [B,H,Lk,d].
+ *   Opartial   [B*H*Lq*d] fp32, normalised by this shard's own row sums;
+ *   LSEpartial [B*H*Lq]   fp32 log-sum-exp of the scaled scores over this shard.
+ * N such partials stored back to back ([N][B*H][Lq][d] / [N][B*H][Lq]) are exactly fa_v2_combine's input. */
+int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opartial, float* LSEpartial, int B, int H,
+                       int Lq, int Lk, int d, int dtype, void* stream);
+
 /* ---- V1 tiled-d -----------------------------------------------------------------------------
  * Replaces  void flash_attention_v1[_opt](..., int d_runtime, int d_tile_qk_runtime, int d_tile_v_runtime)
  *           flash_attention_v1_tiled_d/CUDA/flash_attention_v1.h:312-354, flash_attention_v1_opt.h:448-490.

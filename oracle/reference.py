@@ -27,19 +27,35 @@ def naive_attention_f64(Q, K, V):
                            np.asarray(V, dtype=np.float64))
 
 
-def naive_attention_ex_f64(Q, K, V, causal=False):
-    """Extended oracle for SURVEY.md §8(f)-1 (not in the reference, which defers causal masking,
-    flash_attention_v1/README_v1.md:169): same math as naive_attention with an optional causal mask (row i sees keys
-    0..i) and the per-row log-sum-exp of the scaled scores.  [L,d] float64 -> (O [L,d], LSE [L])."""
+def naive_attention_ex_f64(Q, K, V, causal=False, kv_len=None):
+    """Extended oracle for SURVEY.md §8(f)-1 (not in the reference, which defers "dynamic sequence lengths and causal
+    masking", flash_attention_v1/README_v1.md:169): same math as naive_attention with an optional causal mask (row i
+    sees keys 0..i), an optional key-padding length (only the first kv_len keys are attended to), rectangular shapes
+    (Q [Lq,d], K/V [Lk,d]) and the per-row log-sum-exp of the scaled scores.  float64 -> (O [Lq,d], LSE [Lq])."""
     Q, K, V = (np.asarray(x, dtype=np.float64) for x in (Q, K, V))
-    L, d = Q.shape
+    Lq, d = Q.shape
+    Lk = K.shape[0]
     s = (Q @ K.T) * (1.0 / np.sqrt(d))
     if causal:
-        s = np.where(np.tril(np.ones((L, L), dtype=bool)), s, -np.inf)
+        assert Lq == Lk
+        s = np.where(np.tril(np.ones((Lq, Lk), dtype=bool)), s, -np.inf)
+    if kv_len is not None:
+        s = np.where(np.arange(Lk)[None, :] < kv_len, s, -np.inf)
     m = s.max(axis=1, keepdims=True)
     p = np.exp(s - m)
     l = p.sum(axis=1, keepdims=True)
     return (p / l) @ V, (m + np.log(l))[:, 0]
+
+
+def merge_partials_f64(O_parts, LSE_parts):
+    """Merge of normalised attention partials over disjoint key shards (the reduction of
+    flash_attention_v2/numpy_gpu_like.py:269-288 restated on (O~, LSE)):
+    O = sum_k exp(LSE_k - LSE) O~_k with LSE = log sum_k exp(LSE_k).  [N,...,L,d], [N,...,L] -> [...,L,d]."""
+    O_parts = np.asarray(O_parts, dtype=np.float64)
+    LSE_parts = np.asarray(LSE_parts, dtype=np.float64)
+    m = LSE_parts.max(axis=0)
+    w = np.exp(LSE_parts - m)
+    return (w[..., None] * O_parts).sum(axis=0) / w.sum(axis=0)[..., None]
 
 
 def naive_attention_batched_f64(Q, K, V, heads=None, rows=None):

@@ -71,3 +71,48 @@ def test_tensors_on_a_non_current_device():
     ref = reference.naive_attention_batched_f64(*(x.float().cpu().numpy() for x in (Q, K, V)))
     assert np.abs(O.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
     assert np.abs(O2.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
+
+
+def _ring_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from exploring_flash_attention_b200.sharding import ring_attention
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    B, H, L, d = 1, 3, 1024, 128
+    g = torch.Generator().manual_seed(77)
+    Q, K, V = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
+    Ls = L // world
+    qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous().cuda() for x in (Q, K, V))
+    local = ring_attention(qs, ks, vs)
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    torch.cuda.synchronize()
+    if rank == 0:
+        full = torch.cat(list(out), dim=2)
+        q.put((full.float().cpu().numpy(), Q.float().numpy(), K.float().numpy(), V.float().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_ring_attention_nccl():
+    """Sequence-sharded (context-parallel) attention: K/V shards travel round the NCCL ring, partials merged per rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import reference
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, Q, K, V = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = reference.naive_attention_batched_f64(Q, K, V)
+    assert np.abs(full.reshape(ref.shape) - ref).max() <= 2e-3

@@ -368,3 +368,86 @@ def test_v2_reference_signature_kernels_driver_loop(ops, golden):
     for qt in range(nq):
         reduction_kernel(rO, rm, rl, O2, qt, nkb, L, d, Bq)
     assert np.abs(O2 - Od).max() <= 1e-5
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d,dtype,causal", [
+    (3, 2, 512, 512, 128, torch.bfloat16, False), (3, 2, 512, 512, 128, torch.bfloat16, True),
+    (2, 3, 300, 777, 64, torch.bfloat16, False), (4, 1, 1000, 130, 32, torch.float16, False),
+    (2, 2, 129, 640, 32, torch.float32, False), (3, 2, 700, 700, 64, torch.float32, True),
+    (2, 2, 64, 2048, 128, torch.float16, False),
+])
+def test_key_padding_and_rectangular_match_extended_oracle(ops, B, H, Lq, Lk, d, dtype, causal):
+    """SURVEY.md §8(f)-1 "dynamic sequence lengths": per-batch key-padding lengths and Lq != Lk (fa_v1_forward_varlen)."""
+    g = torch.Generator().manual_seed(11)
+    Q = ((torch.rand((B, H, Lq, d), generator=g) * 2 - 1).to(dtype)).cuda()
+    K, V = (((torch.rand((B, H, Lk, d), generator=g) * 2 - 1).to(dtype)).cuda() for _ in range(2))
+    lens = [Lk, 1, max(1, Lk // 2 + 3), 128][:B]
+    kv_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    for use_lens in (False, True):
+        O, lse = ops.flash_attention_varlen(Q, K, V, kv_lens if use_lens else None, causal=causal, return_lse=True, sync=True)
+        assert not torch.isnan(O).any() and not torch.isnan(lse).any()
+        for b in range(B):
+            for h in range(H):
+                f = lambda x: x[b, h].float().cpu().numpy()
+                ref_o, ref_lse = reference.naive_attention_ex_f64(f(Q), f(K), f(V), causal=causal,
+                                                                  kv_len=lens[b] if use_lens else None)
+                scale = max(1.0, np.abs(ref_o).max() * 2)
+                assert np.abs(O[b, h].float().cpu().numpy() - ref_o).max() <= TOL[dtype] * scale
+                assert np.abs(lse[b, h].cpu().numpy() - ref_lse).max() <= 2e-3
+    if Lq == Lk:   # no mask, square: bit-identical to the plain entry point
+        assert torch.equal(ops.flash_attention_varlen(Q, K, V, sync=True), ops.flash_attention_v1_ex(Q, K, V, sync=True))
+    if not causal:  # out-of-range lengths are clamped to [1, Lk]
+        wild = torch.tensor([10 ** 6, -5, 0, Lk + 1][:B], dtype=torch.int32, device="cuda")
+        Ow = ops.flash_attention_varlen(Q, K, V, wild, sync=True)
+        clamped = torch.tensor([Lk, 1, 1, Lk][:B], dtype=torch.int32, device="cuda")
+        assert torch.equal(Ow, ops.flash_attention_varlen(Q, K, V, clamped, sync=True))
+
+
+@pytest.mark.parametrize("B,H,Lq,d,dtype,shards", [
+    (1, 3, 384, 128, torch.bfloat16, [256, 128, 333]), (2, 2, 200, 64, torch.float16, [64, 1, 500, 129]),
+    (1, 2, 256, 32, torch.float32, [100, 700]),
+])
+def test_partials_over_key_shards_merge_to_full_attention(ops, B, H, Lq, d, dtype, shards):
+    """SURVEY.md §8(f)-2 building block: fa_partial_forward per K/V shard + fa_v2_combine == attention over all keys
+    (what each rank of ring_attention computes)."""
+    g = torch.Generator().manual_seed(13)
+    Lk = sum(shards)
+    Q = ((torch.rand((B, H, Lq, d), generator=g) * 2 - 1).to(dtype)).cuda()
+    K, V = (((torch.rand((B, H, Lk, d), generator=g) * 2 - 1).to(dtype)).cuda() for _ in range(2))
+    o_parts = torch.empty((len(shards), B * H, Lq, d), dtype=torch.float32, device="cuda")
+    lse_parts = torch.empty((len(shards), B * H, Lq), dtype=torch.float32, device="cuda")
+    off = 0
+    f = lambda x: x.float().cpu().numpy()
+    for s, n in enumerate(shards):
+        ks, vs = K[:, :, off:off + n].contiguous(), V[:, :, off:off + n].contiguous()
+        ops.flash_attention_partial(Q, ks, vs, o_parts[s], lse_parts[s])
+        for i in range(B * H):      # each partial against the extended oracle on that shard alone
+            ref_o, ref_lse = reference.naive_attention_ex_f64(f(Q).reshape(-1, Lq, d)[i], f(ks).reshape(-1, n, d)[i],
+                                                              f(vs).reshape(-1, n, d)[i])
+            assert np.abs(o_parts[s, i].cpu().numpy() - ref_o).max() <= TOL[dtype] * max(1.0, np.abs(ref_o).max() * 2)
+            assert np.abs(lse_parts[s, i].cpu().numpy() - ref_lse).max() <= 2e-3
+        off += n
+    O = ops.flash_attention_v2_combine(o_parts, lse_parts, dtype, (B, H, Lq, d))
+    torch.cuda.synchronize()
+    assert not torch.isnan(O).any()
+    for i in range(B * H):
+        ref_o, _ = reference.naive_attention_ex_f64(f(Q).reshape(-1, Lq, d)[i], f(K).reshape(-1, Lk, d)[i], f(V).reshape(-1, Lk, d)[i])
+        assert np.abs(f(O).reshape(-1, Lq, d)[i] - ref_o).max() <= TOL[dtype]
+    # and the oracle's own merge of the GPU partials agrees with the GPU combine
+    merged = reference.merge_partials_f64(o_parts.cpu().numpy(), lse_parts.cpu().numpy())
+    assert np.abs(f(O).reshape(-1, Lq, d) - merged).max() <= TOL[dtype]
+
+
+def test_varlen_and_partial_reject_unsupported(ops):
+    from exploring_flash_attention_b200 import FlashAttentionError
+    Q = torch.zeros((1, 1, 128, 256), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_varlen(Q, Q, Q)
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_partial(Q, Q, Q)
+    q = torch.zeros((1, 1, 128, 64), dtype=torch.bfloat16, device="cuda")
+    k = torch.zeros((1, 1, 256, 64), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_varlen(q, k, k, causal=True)          # causal needs Lq == Lk
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_varlen(q, k, k, torch.ones(3, dtype=torch.int32, device="cuda"))   # kv_lens must have B entries

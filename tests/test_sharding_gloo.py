@@ -57,3 +57,55 @@ def test_two_rank_head_sharding_and_gather():
     ref = reference.naive_attention_batched_f64(Q.numpy(), K.numpy(), V.numpy())
     assert full.shape == (BH, L, d)
     np.testing.assert_allclose(full, ref, atol=1e-6)
+
+
+def _ring_worker(rank, world, port, B, H, L, d, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from exploring_flash_attention_b200.sharding import ring_attention
+    from oracle import reference
+    g = torch.Generator().manual_seed(7)
+    Q, K, V = (torch.rand((B, H, L, d), generator=g) * 2 - 1 for _ in range(3))     # same tensors on every rank
+    Ls = L // world
+    qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous() for x in (Q, K, V))
+
+    def partial_fn(q_, k_, v_, o_out, lse_out):      # oracle stand-in for the CUDA partial kernel
+        for i in range(B * H):
+            o, lse = reference.naive_attention_ex_f64(q_.reshape(-1, Ls, d)[i].numpy(), k_.reshape(-1, Ls, d)[i].numpy(),
+                                                      v_.reshape(-1, Ls, d)[i].numpy())
+            o_out[i] = torch.from_numpy(o).float()
+            lse_out[i] = torch.from_numpy(lse).float()
+
+    def combine_fn(o_parts, lse_parts, dtype, shape):
+        return torch.from_numpy(reference.merge_partials_f64(o_parts.numpy(), lse_parts.numpy())).to(dtype).reshape(shape)
+
+    local = ring_attention(qs, ks, vs, partial_fn=partial_fn, combine_fn=combine_fn)
+    out = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(out, local)
+    if rank == 0:
+        q.put(torch.cat(out, dim=2).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ring_attention_schedule_over_gloo():
+    """Sequence sharded over 3 ranks: every K/V shard must visit every rank exactly once and the merged partials
+    must equal unsharded attention."""
+    B, H, L, d, world = 1, 2, 36, 8, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, B, H, L, d, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, str(ROOT))
+    from oracle import reference
+    g = torch.Generator().manual_seed(7)
+    Q, K, V = (torch.rand((B, H, L, d), generator=g) * 2 - 1 for _ in range(3))
+    ref = reference.naive_attention_batched_f64(Q.numpy(), K.numpy(), V.numpy())
+    np.testing.assert_allclose(full.reshape(B * H, L, d), ref, atol=1e-5)

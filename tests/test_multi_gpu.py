@@ -73,7 +73,7 @@ def test_tensors_on_a_non_current_device():
     assert np.abs(O2.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
 
 
-def _ring_worker(rank, world, port, q):
+def _ring_worker(rank, world, port, q, transport="nccl"):
     sys.path.insert(0, str(ROOT))
     import torch.distributed as dist
     from exploring_flash_attention_b200.sharding import ring_attention
@@ -85,7 +85,9 @@ def _ring_worker(rank, world, port, q):
     Q, K, V = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
     Ls = L // world
     qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous().cuda() for x in (Q, K, V))
-    local = ring_attention(qs, ks, vs)
+    local = ring_attention(qs, ks, vs, transport=transport)
+    if transport == "peer":   # second call reuses the cached symmetric buffers (restaging must not race the last pull)
+        assert torch.equal(local, ring_attention(qs, ks, vs, transport=transport))
     out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local)
     torch.cuda.synchronize()
@@ -96,8 +98,10 @@ def _ring_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_ring_attention_nccl():
-    """Sequence-sharded (context-parallel) attention: K/V shards travel round the NCCL ring, partials merged per rank."""
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
+def test_two_gpu_ring_attention(transport):
+    """Sequence-sharded (context-parallel) attention: K/V shards travel round the ring (NCCL send/recv, or copy-engine
+    pulls out of the neighbour's symmetric-memory buffer), partials merged per rank."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -107,7 +111,7 @@ def test_two_gpu_ring_attention_nccl():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q, transport)) for r in range(2)]
     for p in procs:
         p.start()
     full, Q, K, V = q.get(timeout=300)

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -241,7 +242,13 @@ struct HostStaging {
   size_t bytes = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  static constexpr int kChunks = 8;       // head chunks in flight through the H2D / compute / D2H pipeline
+#ifndef FA_HOST_CHUNKS
+#define FA_HOST_CHUNKS 8
+#endif
+#ifndef FA_HOST_GEOMETRIC
+#define FA_HOST_GEOMETRIC 1
+#endif
+  static constexpr int kChunks = FA_HOST_CHUNKS;  // head chunks in flight through the H2D / compute / D2H pipeline
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_h2d[kChunks] = {}, ev_comp[kChunks] = {};
   bool streams_ready = false;
@@ -430,11 +437,31 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
   }
   cudaStream_t s_h2d = g_stage.stream[0], s_comp = g_stage.stream[1], s_d2h = g_stage.stream[2];
   const int BH = B * H;
-  const int n_chunks = BH < HostStaging::kChunks ? BH : HostStaging::kChunks;
+  // Chunk sizes halve (1/2, 1/4, ... of the heads, the last two equal): every cudaMemcpyAsync costs ~12 us of copy-
+  // engine set-up, so few large copies up front, and a small last chunk so little D2H is left when the H2D stream ends.
+  int bounds[HostStaging::kChunks + 1];
+  int n_chunks = 0;
+  bounds[0] = 0;
+#if FA_HOST_GEOMETRIC
+  {
+    const int floor_heads = BH / 16 > 0 ? BH / 16 : 1;
+    int done = 0;
+    while (done < BH) {
+      int take = (BH - done + 1) / 2;
+      if (take < floor_heads || n_chunks == HostStaging::kChunks - 1) take = BH - done;
+      done += take;
+      bounds[++n_chunks] = done;
+    }
+  }
+#else
+  n_chunks = BH < HostStaging::kChunks ? BH : HostStaging::kChunks;
+  for (int c = 1; c <= n_chunks; ++c) bounds[c] = int((long long)BH * c / n_chunks);
+#endif
   const size_t head_bytes = size_t(L) * d * elem_size(dtype);
   size_t ws_need = 0;
   if (variant == 2) {
-    const int max_heads = (BH + n_chunks - 1) / n_chunks;
+    int max_heads = 0;
+    for (int c = 0; c < n_chunks; ++c) max_heads = std::max(max_heads, bounds[c + 1] - bounds[c]);
     ws_need = fa_v2_workspace_bytes(1, max_heads, L, d, kv_per_split);
     if (ws_need == 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
     if (ws_need > g_stage.ws_bytes) {
@@ -446,7 +473,7 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
     }
   }
   for (int c = 0; c < n_chunks; ++c) {
-    const int h0 = int((long long)BH * c / n_chunks), h1 = int((long long)BH * (c + 1) / n_chunks);
+    const int h0 = bounds[c], h1 = bounds[c + 1];
     const int nh = h1 - h0;
     if (nh == 0) continue;
     const size_t off = size_t(h0) * head_bytes, cb = size_t(nh) * head_bytes;

@@ -21,10 +21,36 @@ while time.time() < t_end:
     if d >= 256:
         L = min(L, 1024)
     BH = rng.choice([1, 2, 3, 5, 37, 149, 300]) if L <= 300 else rng.choice([1, 2, 3, 5, 19])
-    variant = rng.choice(["v1", "v1", "v2"]) if d <= 128 else "td"
+    variant = rng.choice(["v1", "v1", "v2", "varlen", "causal", "parts"]) if d <= 128 else "td"
     g = torch.Generator().manual_seed(n)
     Q, K, V = ((torch.rand((1, BH, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
-    if variant == "v1":
+    mask = None          # [BH, Lq, Lk] bool of attended keys, when the variant masks
+    if variant == "varlen":
+        # heads become batch entries so every head gets its own key-padding length; K/V get their own length too
+        Lk = rng.choice([1, 64, 129, 300, 1024, L])
+        K, V = ((torch.rand((1, BH, Lk, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(2))
+        lens = torch.tensor([rng.randint(1, Lk) for _ in range(BH)], dtype=torch.int32, device="cuda")
+        O = ops.flash_attention_varlen(Q.reshape(BH, 1, L, d), K.reshape(BH, 1, Lk, d), V.reshape(BH, 1, Lk, d), lens,
+                                       sync=True).reshape(1, BH, L, d)
+        mask = (torch.arange(Lk, device="cuda")[None, None, :] < lens[:, None, None]).expand(BH, L, Lk)
+        tag = f"varlen/Lk{Lk}"
+    elif variant == "causal":
+        O = ops.flash_attention_v1_ex(Q, K, V, causal=True, sync=True)
+        mask = torch.ones((L, L), dtype=torch.bool, device="cuda").tril()[None].expand(BH, L, L)
+        tag = "causal"
+    elif variant == "parts":
+        # key shards of random sizes -> partials -> combine (what one rank of ring_attention does)
+        cuts = sorted(set(rng.sample(range(1, L), min(L - 1, rng.randint(1, 4))))) if L > 1 else []
+        bounds = [0] + cuts + [L]
+        o_parts = torch.empty((len(bounds) - 1, BH, L, d), dtype=torch.float32, device="cuda")
+        lse_parts = torch.empty((len(bounds) - 1, BH, L), dtype=torch.float32, device="cuda")
+        for si in range(len(bounds) - 1):
+            ops.flash_attention_partial(Q, K[:, :, bounds[si]:bounds[si + 1]].contiguous(),
+                                        V[:, :, bounds[si]:bounds[si + 1]].contiguous(), o_parts[si], lse_parts[si])
+        O = ops.flash_attention_v2_combine(o_parts, lse_parts, dtype, (1, BH, L, d))
+        torch.cuda.synchronize()
+        tag = f"parts/{len(bounds) - 1}"
+    elif variant == "v1":
         O = ops.flash_attention_v1(Q, K, V, sync=True)
         tag = "v1"
     elif variant == "td":
@@ -37,7 +63,10 @@ while time.time() < t_end:
     nh = min(BH, 4)
     idx = torch.tensor(sorted(rng.sample(range(BH), nh)), device="cuda")
     q, k, v = (x[0, idx].double() for x in (Q, K, V))
-    ref = torch.softmax(q @ k.transpose(-1, -2) / d ** 0.5, -1) @ v
+    sc = q @ k.transpose(-1, -2) / d ** 0.5
+    if mask is not None:
+        sc = sc.masked_fill(~mask[idx], float("-inf"))
+    ref = torch.softmax(sc, -1) @ v
     err = (O[0, idx].double() - ref).abs().max().item()
     key = (str(dtype), d)
     worst[key] = max(worst.get(key, 0.0), err)

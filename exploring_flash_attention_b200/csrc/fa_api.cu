@@ -67,7 +67,8 @@ int sm_count() {
 
 // [BH][L][D] row-major tensor, box = one 128-byte-wide, `box_rows`-row block of one head, 128B swizzle.
 // Rows past L are zero-filled on load and clipped on store, so tiles never leak into the next head.
-int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false) {
+int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false,
+             long long head_stride_rows = 0 /* rows between consecutive heads; 0 = L (dense) */) {
   EncodeFn enc = get_encode_fn();
   if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = elem_size(dtype);
@@ -75,7 +76,7 @@ int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, i
                            : dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t dims[3] = {cuuint64_t(D), cuuint64_t(L), cuuint64_t(BH)};
-  cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(L) * D * es};
+  cuuint64_t strides[2] = {cuuint64_t(D) * es, cuuint64_t(head_stride_rows > 0 ? head_stride_rows : L) * D * es};
   const int swb = (D * es >= 128) ? 128 : 64;  // swizzle span = bytes of one block row (64 only for 16-bit d = 32)
   cuuint32_t box[3] = {cuuint32_t(swb / es), cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -105,6 +106,8 @@ struct FwdExtra {
   int Lk = 0;                    // keys per head when it differs from the query count (0: same as L)
   int H = 0;                     // heads per batch entry (needed with kv_lens)
   const int* kv_lens = nullptr;  // device [B] int32 key-padding lengths
+  // Row windows of taller tensors (rows between consecutive heads; 0 = dense).  The row offset is in the pointer.
+  long long q_head_rows = 0, kv_head_rows = 0, out_head_rows = 0;
 };
 
 template <int D, int DT, bool SPLIT>
@@ -115,15 +118,15 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   const int Lk = ex.Lk > 0 ? ex.Lk : L;
-  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmK, K, DT, D, Lk, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmV, V, DT, D, Lk, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128, false, ex.q_head_rows)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, Lk, BH, 128, false, ex.kv_head_rows)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, Lk, BH, 128, /*mn_major_operand=*/true, ex.kv_head_rows)) != FA_OK) return rc;
   if (SPLIT) {
     tmO = tmQ;  // unused by the split epilogue
   } else if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) {
     return rc;
   }
-  fa::FwdParams p;
+  fa::FwdParams p{};
   p.L = L;
   p.Lk = Lk;
   p.BH = BH;
@@ -140,7 +143,8 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.o_accum = o_accum;
   p.lse_accum = lse_accum;
   p.lse_out = SPLIT ? nullptr : lse_out;
-  p.causal = SPLIT ? 0 : causal;
+  p.causal = (SPLIT && (n_splits != 1 || Lk != L)) ? 0 : causal;
+  p.out_head_rows = int(ex.out_head_rows > 0 ? ex.out_head_rows : L);
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...
@@ -183,7 +187,7 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
   if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
   if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) return rc;
-  fa::FwdParams p;
+  fa::FwdParams p{};
   p.L = L;
   p.BH = BH;
   p.kv_per_split = L;
@@ -305,18 +309,28 @@ int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, f
 }
 
 int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opartial, float* LSEpartial, int B, int H,
-                       int Lq, int Lk, int d, int dtype, void* stream) {
+                       int Lq, int Lk, int d, int dtype, long long q_head_rows, long long kv_head_rows,
+                       long long out_head_rows, unsigned flags, void* stream) {
   int rc = check_common(Q, K, V, Opartial, B, H, Lq, d, dtype);
   if (rc != FA_OK) return rc;
   if (Lk <= 0) return fail(FA_ERR_SHAPE, "Lk must be positive");
   if (LSEpartial == nullptr) return fail(FA_ERR_ALIGN, "LSEpartial must be non-null");
+  if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
+  if ((flags & FA_FLAG_CAUSAL) && Lq != Lk) return fail(FA_ERR_SHAPE, "causal masking needs Lq == Lk");
+  if ((q_head_rows != 0 && q_head_rows < Lq) || (kv_head_rows != 0 && kv_head_rows < Lk) ||
+      (out_head_rows != 0 && out_head_rows < Lq))
+    return fail(FA_ERR_SHAPE, "head strides (in rows) must be 0 (dense) or at least the row count");
+  if (out_head_rows > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "out_head_rows too large");
   if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
     return fail(FA_ERR_UNSUPPORTED_D, "partial attention is served by the fused-tile kernel only (row of at most 256 bytes)");
   FwdExtra ex;
   ex.Lk = Lk;
   ex.H = H;
+  ex.q_head_rows = q_head_rows;
+  ex.kv_head_rows = kv_head_rows;
+  ex.out_head_rows = out_head_rows;
   return dispatch_fwd<true>(Q, K, V, nullptr, B * H, Lq, d, dtype, /*kv_per_split=*/Lk, /*n_splits=*/1, Opartial,
-                            LSEpartial, static_cast<cudaStream_t>(stream), nullptr, 0, ex);
+                            LSEpartial, static_cast<cudaStream_t>(stream), nullptr, (flags & FA_FLAG_CAUSAL) ? 1 : 0, ex);
 }
 
 int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,

@@ -52,7 +52,9 @@ struct FwdParams {
   float* o_accum;    // [n_splits][BH][L][D] fp32, each split normalised by its own l   (SPLIT only)
   float* lse_accum;  // [n_splits][BH][L]    fp32, m/sqrt(d) + ln(l)                     (SPLIT only)
   float* lse_out;    // optional [BH][L] fp32: log-sum-exp of the scaled scores of each row      (non-SPLIT, may be null)
-  int causal;        // != 0: query row r attends to keys 0..r only                            (non-SPLIT)
+  int causal;        // != 0: query row r attends to keys 0..r only   (SPLIT: only with n_splits == 1 and L == Lk)
+  int out_head_rows; // SPLIT: rows between consecutive heads of o_accum / lse_accum (== L unless the caller writes into a
+                     // row window of a taller partial buffer)
 };
 
 // (Tried and dropped: O rows straight from registers to global to buy a 5th K/V ring stage — the row-strided 16-byte
@@ -136,7 +138,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   ItemCoord c;
   int qp = item % p.n_qpairs;
   int rest = item / p.n_qpairs;
-  if (!SPLIT && p.causal) {
+  if (p.causal) {
     // Causal items grow with the q-pair index.  Order ALL items longest-first (q-pair descending, head fastest) so the
     // static round-robin over CTAs is an LPT schedule; head-major order would hand every CTA the same q-pair index
     // whenever gridDim.x is a multiple of n_qpairs.
@@ -153,7 +155,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   c.n_tiles = (c.kv_end - c.kv_begin + 127) / 128;
   c.n_q = (p.L - c.q_row0 > 128) ? 2 : 1;
   c.nt[0] = c.nt[1] = c.n_tiles;
-  if (!SPLIT && p.causal) {
+  if (p.causal) {
     c.nt[0] = min(c.n_tiles, c.q_row0 / 128 + 1);
     c.nt[1] = min(c.n_tiles, c.q_row0 / 128 + 2);
     c.n_tiles = c.n_q > 1 ? c.nt[1] : c.nt[0];
@@ -452,7 +454,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // valid = number of leading columns of this tile my row may attend to: the ragged end of the key range and,
         // when causal, the diagonal (key index <= query row); only the last tile of a row can be cut.
         int valid = c.kv_end - (c.kv_begin + j * BN);
-        if (!SPLIT && p.causal) valid = min(valid, row_q - j * BN + 1);
+        if (p.causal) valid = min(valid, row_q - j * BN + 1);
         float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
         if (__all_sync(0xffffffffu, valid >= BN)) {
 #pragma unroll
@@ -600,7 +602,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         p.lse_out[size_t(c.bh) * p.L + row_g] = m_used * p.scale + __logf(l);
       if constexpr (SPLIT) {
         if (row_g < p.L) {
-          const size_t ridx = (size_t(c.split) * p.BH + c.bh) * p.L + row_g;
+          const size_t ridx = (size_t(c.split) * p.BH + c.bh) * p.out_head_rows + row_g;
           p.lse_accum[ridx] = m_used * p.scale + __logf(l);
           float* dst = p.o_accum + ridx * D;
 #pragma unroll

@@ -115,23 +115,46 @@ def flash_attention_varlen(Q, K, V, kv_lens=None, O=None, causal: bool = False, 
     return (O, lse) if return_lse else O
 
 
+def _head_rows(x, what):
+    """x: [B,H,L,d] (or [BH,L,d]) whose rows are dense and whose heads are evenly spaced (a contiguous tensor or a
+    window x[..., r0:r1, :] of one).  Returns the spacing of consecutive heads in rows."""
+    L, d = x.shape[-2:]
+    st = x.stride()
+    ok = st[-1] == 1 and st[-2] == d and st[-3] % d == 0 and st[-3] >= L * d
+    if ok and x.dim() == 4 and x.shape[0] > 1:
+        ok = st[0] == x.shape[1] * st[1]
+    if not ok or x.dim() not in (3, 4):
+        raise _lib.FlashAttentionError(-3, f"{what} must be contiguous or a row window of a contiguous [B,H,L,d] tensor")
+    return st[-3] // d
+
+
 @_on_device_of
-def flash_attention_partial(Q, K, V, Opartial=None, LSEpartial=None):
+def flash_attention_partial(Q, K, V, Opartial=None, LSEpartial=None, causal: bool = False):
     """One un-merged attention partial: Q [B,H,Lq,d] against one key/value shard [B,H,Lk,d].
     Returns (Opartial [B*H,Lq,d] fp32 normalised by the shard's own row sums, LSEpartial [B*H,Lq] fp32);
-    partials stacked on a leading axis are flash_attention_v2_combine's input."""
-    Q, K, V = _prep_rect(Q, K, V)
+    partials stacked on a leading axis are flash_attention_v2_combine's input.  Q, K, V and the outputs may be row
+    windows (x[:, :, r0:r1]) of taller contiguous tensors; causal=True (Lq == Lk) masks keys above the diagonal."""
+    if not (Q.is_cuda and K.is_cuda and V.is_cuda):
+        raise RuntimeError("flash-attention B200 path needs CUDA tensors: there is no CPU fallback")
+    if Q.dtype not in _DTYPES or not (Q.dtype == K.dtype == V.dtype):
+        raise _lib.FlashAttentionError(-2, "Q, K, V must share a supported dtype")
+    if Q.dim() != 4 or K.dim() != 4 or K.shape != V.shape or Q.shape[:2] != K.shape[:2] or Q.shape[3] != K.shape[3]:
+        raise _lib.FlashAttentionError(-1, "Q must be [B,H,Lq,d] and K, V [B,H,Lk,d]")
     B, H, Lq, d = Q.shape
     Lk = K.shape[2]
     if Opartial is None:
         Opartial = torch.empty((B * H, Lq, d), dtype=torch.float32, device=Q.device)
     if LSEpartial is None:
         LSEpartial = torch.empty((B * H, Lq), dtype=torch.float32, device=Q.device)
-    if not (Opartial.is_contiguous() and LSEpartial.is_contiguous()):
-        raise _lib.FlashAttentionError(-3, "Opartial / LSEpartial must be contiguous")
+    q_rows, k_rows, v_rows, o_rows = (_head_rows(x, n) for x, n in ((Q, "Q"), (K, "K"), (V, "V"), (Opartial, "Opartial")))
+    lse_ok = LSEpartial.stride(-1) == 1 and LSEpartial.dtype == torch.float32 and \
+        (LSEpartial.numel() == LSEpartial.shape[-1] or LSEpartial.stride(-2) == o_rows)
+    if k_rows != v_rows or not lse_ok or Opartial.dtype != torch.float32:
+        raise _lib.FlashAttentionError(-3, "K and V must share a layout; LSEpartial must be fp32 with Opartial's head spacing")
     lib = _lib.load()
     _lib.check(lib.fa_partial_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), Opartial.data_ptr(),
-                                      LSEpartial.data_ptr(), B, H, Lq, Lk, d, _DTYPES[Q.dtype], _stream()))
+                                      LSEpartial.data_ptr(), B, H, Lq, Lk, d, _DTYPES[Q.dtype], q_rows, k_rows, o_rows,
+                                      1 if causal else 0, _stream()))
     return Opartial, LSEpartial
 
 

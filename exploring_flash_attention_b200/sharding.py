@@ -67,13 +67,41 @@ def _peer_ring(shape, dtype, device, group):
     return _peer_rings[key]
 
 
-def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None, partial_fn=None, combine_fn=None,
-                   transport: str = "auto"):
-    """Non-causal attention over a sequence sharded across the ranks of `group`.
+def zigzag_shard(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """[..., L, d] -> this rank's causal-ring shard: chunks r and 2N-1-r of the 2N equal chunks of the sequence,
+    concatenated (so every rank owns one early and one late chunk and causal work is balanced)."""
+    L = x.shape[-2]
+    if L % (2 * world) != 0:
+        raise ValueError("sequence length must be a multiple of 2 * world size")
+    C = L // (2 * world)
+    return torch.cat([x[..., rank * C:(rank + 1) * C, :], x[..., (2 * world - 1 - rank) * C:(2 * world - rank) * C, :]],
+                     dim=-2)
 
-    Q, K, V: this rank's [B,H,Ls,d] shards (same Ls on every rank, sequence split in rank order).  Returns this rank's
-    [B,H,Ls,d] rows of softmax(Q_all K_all^T / sqrt(d)) V_all.  Step s computes the partial of the local queries
-    against the shard that started on rank (r - s) mod N while the next shard is already on its way.
+
+def zigzag_unshard(shards) -> torch.Tensor:
+    """Inverse of zigzag_shard: the per-rank [..., 2C, d] shards (in rank order) -> the [..., L, d] sequence."""
+    world = len(shards)
+    C = shards[0].shape[-2] // 2
+    chunks = [None] * (2 * world)
+    for r, sh in enumerate(shards):
+        chunks[r] = sh[..., :C, :]
+        chunks[2 * world - 1 - r] = sh[..., C:, :]
+    return torch.cat(chunks, dim=-2)
+
+
+def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None, partial_fn=None, combine_fn=None,
+                   transport: str = "auto", causal: bool = False):
+    """Attention over a sequence sharded across the ranks of `group`.
+
+    Q, K, V: this rank's [B,H,Ls,d] shards (same Ls on every rank).  Returns this rank's [B,H,Ls,d] rows of
+    softmax(Q_all K_all^T / sqrt(d)) V_all.  Step s computes the partial of the local queries against the shard that
+    started on rank (r - s) mod N while the next shard is already on its way.
+
+    causal=False: the sequence is split in rank order (rank r owns rows [r*Ls, (r+1)*Ls)).
+    causal=True:  zig-zag layout (`zigzag_shard`): rank r owns chunks r and 2N-1-r of 2N chunks.  Step 0 is plain
+      causal attention over the local shard; a shard from a lower rank j contributes its early chunk to all local
+      queries; a shard from a higher rank contributes both chunks to the late local queries only — every step is
+      half a dense block, so all ranks do the same work.
 
     transport "nccl": send/recv pairs on the communicator's stream (works on any backend; its kernels need SMs, so
       under the persistent attention kernel the hop is mostly exposed: 10.9 ms at L=16384 on 8 GPUs).
@@ -100,6 +128,22 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
     B, H, Ls, d = Q.shape
     o_parts = torch.empty((world, B * H, Ls, d), dtype=torch.float32, device=Q.device)
     lse_parts = torch.empty((world, B * H, Ls), dtype=torch.float32, device=Q.device)
+    if causal and Ls % 2 != 0:
+        raise ValueError("causal ring attention needs an even number of local rows (two zig-zag chunks)")
+    C = Ls // 2
+
+    def step(s, k, v):
+        """Partial of the local queries against the shard (k, v) that started on rank (rank - s) mod world -> slot s."""
+        if not causal:
+            partial_fn(Q, k, v, o_parts[s], lse_parts[s])
+        elif s == 0:
+            partial_fn(Q, k, v, o_parts[0], lse_parts[0], causal=True)
+        elif (rank - s) % world < rank:
+            partial_fn(Q, k[:, :, :C], v[:, :, :C], o_parts[s], lse_parts[s])
+        else:
+            partial_fn(Q[:, :, C:], k, v, o_parts[s][:, C:], lse_parts[s][:, C:])
+            o_parts[s][:, :C].zero_()                       # early queries see nothing of a later rank's shard:
+            lse_parts[s][:, :C].fill_(float("-inf"))        # weight exp(-inf) = 0 in the merge
 
     if transport == "peer" and world > 1:
         buf, hdl, copy_stream = _peer_ring((2, B, H, Ls, d), Q.dtype, Q.device, group)
@@ -119,7 +163,7 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
                     buf[1 - cur].copy_(src, non_blocking=True)
                     arrived = torch.cuda.Event()
                     arrived.record(copy_stream)
-            partial_fn(Q, buf[cur, 0], buf[cur, 1], o_parts[s], lse_parts[s])
+            step(s, buf[cur, 0], buf[cur, 1])
             if arrived is not None:
                 main.wait_event(arrived)
                 cur = 1 - cur
@@ -137,7 +181,7 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
             # by the previous step's kernel) is quiescent; runs on the communicator's stream beside this step's kernel
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, kv, send_to, group),
                                            dist.P2POp(dist.irecv, nxt, recv_from, group)])
-        partial_fn(Q, kv[0], kv[1], o_parts[s], lse_parts[s])
+        step(s, kv[0], kv[1])
         for r in reqs:
             r.wait()
         if s + 1 < world:

@@ -74,9 +74,14 @@ int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, f
  * flash_attention_v2/README.md:5-21): queries [B,H,Lq,d] against ONE shard of keys/values [B,H,Lk,d].
  *   Opartial   [B*H*Lq*d] fp32, normalised by this shard's own row sums;
  *   LSEpartial [B*H*Lq]   fp32 log-sum-exp of the scaled scores over this shard.
- * N such partials stored back to back ([N][B*H][Lq][d] / [N][B*H][Lq]) are exactly fa_v2_combine's input. */
+ * N such partials stored back to back ([N][B*H][Lq][d] / [N][B*H][Lq]) are exactly fa_v2_combine's input.
+ *   q_head_rows / kv_head_rows / out_head_rows: rows between consecutive (b,h) heads of Q / K,V / the partial buffers,
+ *           0 = dense.  With the row offset folded into the pointers this addresses a row window of taller tensors
+ *           (e.g. the late half of the local queries against the early half of a neighbour's keys in a zig-zag ring).
+ *   flags   FA_FLAG_CAUSAL (needs Lq == Lk): row i attends to keys 0..i of this shard (the diagonal block). */
 int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opartial, float* LSEpartial, int B, int H,
-                       int Lq, int Lk, int d, int dtype, void* stream);
+                       int Lq, int Lk, int d, int dtype, long long q_head_rows, long long kv_head_rows,
+                       long long out_head_rows, unsigned flags, void* stream);
 
 /* ---- V1 tiled-d -----------------------------------------------------------------------------
  * Replaces  void flash_attention_v1[_opt](..., int d_runtime, int d_tile_qk_runtime, int d_tile_v_runtime)

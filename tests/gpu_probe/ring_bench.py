@@ -49,24 +49,36 @@ def no_comm():
     return ops.flash_attention_v2_combine(o_parts, lse_parts, Q.dtype, (B, H, Ls, d))
 
 
-transport = os.environ.get("RING_TRANSPORT", "nccl")
-ms_ring = timed(lambda: ring_attention(Q, K, V, transport=transport))
+transport = os.environ.get("RING_TRANSPORT", "peer")
+causal = os.environ.get("RING_CAUSAL", "0") == "1"     # zig-zag layout: the local shard is chunks r and 2N-1-r
+ms_ring = timed(lambda: ring_attention(Q, K, V, transport=transport, causal=causal))
 ms_nocomm = timed(no_comm)
-O = ring_attention(Q, K, V, transport=transport)
+O = ring_attention(Q, K, V, transport=transport, causal=causal)
 # check a few rows of head 0 against float64 over the gathered keys
 Kall = torch.empty((world,) + tuple(K.shape), dtype=K.dtype, device="cuda")
 Vall = torch.empty_like(Kall)
 dist.all_gather_into_tensor(Kall, K)
 dist.all_gather_into_tensor(Vall, V)
-kf = torch.cat([Kall[r][0, 0] for r in range(world)]).double()
-vf = torch.cat([Vall[r][0, 0] for r in range(world)]).double()
-rows = slice(0, min(Ls, 256))
-ref = torch.softmax(Q[0, 0, rows].double() @ kf.T / d ** 0.5, dim=-1) @ vf
+if causal:
+    from exploring_flash_attention_b200.sharding import zigzag_unshard
+    kf = zigzag_unshard([Kall[r][0, 0] for r in range(world)]).double()
+    vf = zigzag_unshard([Vall[r][0, 0] for r in range(world)]).double()
+    rows = slice(Ls - min(Ls // 2, 256), Ls)              # late rows of the late chunk: global rows (2N-1-r)*C + ...
+    C = Ls // 2
+    grow = (2 * world - 1 - rank) * C + torch.arange(C - (rows.stop - rows.start), C, device="cuda")
+    sc = Q[0, 0, rows].double() @ kf.T / d ** 0.5
+    sc = sc.masked_fill(torch.arange(L, device="cuda")[None, :] > grow[:, None], float("-inf"))
+    ref = torch.softmax(sc, dim=-1) @ vf
+else:
+    kf = torch.cat([Kall[r][0, 0] for r in range(world)]).double()
+    vf = torch.cat([Vall[r][0, 0] for r in range(world)]).double()
+    rows = slice(0, min(Ls, 256))
+    ref = torch.softmax(Q[0, 0, rows].double() @ kf.T / d ** 0.5, dim=-1) @ vf
 err = torch.tensor([(O[0, 0, rows].double() - ref).abs().max().item()], device="cuda")
 dist.all_reduce(err, op=dist.ReduceOp.MAX)
 if rank == 0:
-    flops = 4.0 * B * H * L * L * d
-    print(json.dumps({"ring_attention": {"B": B, "H": H, "L": L, "d": d, "n_gpus": world, "transport": transport, "ms": ms_ring,
+    flops = 4.0 * B * H * L * L * d * (0.5 if causal else 1.0)
+    print(json.dumps({"ring_attention": {"B": B, "H": H, "L": L, "d": d, "n_gpus": world, "transport": transport, "causal": causal, "ms": ms_ring,
                                          "tflops_total": flops / ms_ring / 1e9, "ms_same_kernels_no_comm": ms_nocomm,
                                          "kv_bytes_per_hop": 2 * B * H * Ls * d * 2, "max_abs_err": err.item()}}), flush=True)
 dist.barrier()

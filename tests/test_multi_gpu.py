@@ -73,10 +73,10 @@ def test_tensors_on_a_non_current_device():
     assert np.abs(O2.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
 
 
-def _ring_worker(rank, world, port, q, transport="nccl"):
+def _ring_worker(rank, world, port, q, transport="nccl", causal=False):
     sys.path.insert(0, str(ROOT))
     import torch.distributed as dist
-    from exploring_flash_attention_b200.sharding import ring_attention
+    from exploring_flash_attention_b200.sharding import ring_attention, zigzag_shard
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -84,39 +84,49 @@ def _ring_worker(rank, world, port, q, transport="nccl"):
     g = torch.Generator().manual_seed(77)
     Q, K, V = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
     Ls = L // world
-    qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous().cuda() for x in (Q, K, V))
-    local = ring_attention(qs, ks, vs, transport=transport)
+    if causal:
+        qs, ks, vs = (zigzag_shard(x, rank, world).contiguous().cuda() for x in (Q, K, V))
+    else:
+        qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous().cuda() for x in (Q, K, V))
+    local = ring_attention(qs, ks, vs, transport=transport, causal=causal)
     if transport == "peer":   # second call reuses the cached symmetric buffers (restaging must not race the last pull)
-        assert torch.equal(local, ring_attention(qs, ks, vs, transport=transport))
+        assert torch.equal(local, ring_attention(qs, ks, vs, transport=transport, causal=causal))
     out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local)
     torch.cuda.synchronize()
     if rank == 0:
-        full = torch.cat(list(out), dim=2)
-        q.put((full.float().cpu().numpy(), Q.float().numpy(), K.float().numpy(), V.float().numpy()))
+        q.put((out.float().cpu().numpy(), Q.float().numpy(), K.float().numpy(), V.float().numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["nccl", "peer"])
-def test_two_gpu_ring_attention(transport):
+@pytest.mark.parametrize("transport,causal", [("nccl", False), ("peer", False), ("peer", True), ("nccl", True)])
+def test_two_gpu_ring_attention(transport, causal):
     """Sequence-sharded (context-parallel) attention: K/V shards travel round the ring (NCCL send/recv, or copy-engine
-    pulls out of the neighbour's symmetric-memory buffer), partials merged per rank."""
+    pulls out of the neighbour's symmetric-memory buffer), partials merged per rank; causal uses the zig-zag layout."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
+    from exploring_flash_attention_b200.sharding import zigzag_unshard
     from oracle import reference
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q, transport)) for r in range(2)]
+    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q, transport, causal)) for r in range(2)]
     for p in procs:
         p.start()
-    full, Q, K, V = q.get(timeout=300)
+    shards, Q, K, V = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    ref = reference.naive_attention_batched_f64(Q, K, V)
-    assert np.abs(full.reshape(ref.shape) - ref).max() <= 2e-3
+    if causal:
+        full = zigzag_unshard([torch.from_numpy(x) for x in shards]).numpy()
+        ref = np.stack([reference.naive_attention_ex_f64(Q[0, h], K[0, h], V[0, h], causal=True)[0] for h in range(Q.shape[1])])
+        tol = 2e-3 * max(1.0, 2 * np.abs(ref).max())      # the first causal rows are O(1)
+    else:
+        full = np.concatenate(list(shards), axis=2)
+        ref = reference.naive_attention_batched_f64(Q, K, V)
+        tol = 2e-3
+    assert np.abs(full.reshape(ref.shape) - ref).max() <= tol

@@ -438,6 +438,41 @@ def test_partials_over_key_shards_merge_to_full_attention(ops, B, H, Lq, d, dtyp
     assert np.abs(f(O).reshape(-1, Lq, d) - merged).max() <= TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 32)])
+def test_partial_causal_and_row_windows(ops, dtype, d):
+    """The zig-zag ring's building blocks: a causal partial (the diagonal block) and partials whose Q / K,V / outputs
+    are row windows of taller tensors, merged into causal attention over the whole local sequence."""
+    B, H, C = 2, 2, 192
+    g = torch.Generator().manual_seed(17)
+    Q, K, V = (((torch.rand((B, H, 2 * C, d), generator=g) * 2 - 1).to(dtype)).cuda() for _ in range(3))
+    f = lambda x: x.float().cpu().numpy().reshape(B * H, -1, d)
+    # (1) causal partial over the whole local sequence == extended oracle
+    o_c, lse_c = ops.flash_attention_partial(Q, K, V, causal=True)
+    torch.cuda.synchronize()
+    for i in range(B * H):
+        ref_o, ref_lse = reference.naive_attention_ex_f64(f(Q)[i], f(K)[i], f(V)[i], causal=True)
+        assert np.abs(o_c[i].cpu().numpy() - ref_o).max() <= TOL[dtype] * max(1.0, 2 * np.abs(ref_o).max())
+        assert np.abs(lse_c[i].cpu().numpy() - ref_lse).max() <= 2e-3
+    # (2) the same thing assembled from windows: [early q x early k causal] [late q x early k full] [late q x late k causal]
+    o_parts = torch.zeros((2, B * H, 2 * C, d), dtype=torch.float32, device="cuda")
+    lse_parts = torch.full((2, B * H, 2 * C), float("-inf"), dtype=torch.float32, device="cuda")
+    ops.flash_attention_partial(Q[:, :, :C], K[:, :, :C], V[:, :, :C], o_parts[0][:, :C], lse_parts[0][:, :C], causal=True)
+    ops.flash_attention_partial(Q[:, :, C:], K[:, :, :C], V[:, :, :C], o_parts[0][:, C:], lse_parts[0][:, C:])
+    ops.flash_attention_partial(Q[:, :, C:], K[:, :, C:], V[:, :, C:], o_parts[1][:, C:], lse_parts[1][:, C:], causal=True)
+    O = ops.flash_attention_v2_combine(o_parts, lse_parts, dtype, (B, H, 2 * C, d))
+    Oc = ops.flash_attention_v1_ex(Q, K, V, causal=True, sync=True)
+    torch.cuda.synchronize()
+    assert not torch.isnan(O).any()
+    for i in range(B * H):
+        ref_o, _ = reference.naive_attention_ex_f64(f(Q)[i], f(K)[i], f(V)[i], causal=True)
+        assert np.abs(f(O)[i] - ref_o).max() <= TOL[dtype] * max(1.0, 2 * np.abs(ref_o).max())
+    assert (O.float() - Oc.float()).abs().max().item() <= 2 * TOL[dtype]
+    # a transposed (non-window) layout is refused rather than misread
+    from exploring_flash_attention_b200 import FlashAttentionError
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_partial(Q.transpose(1, 2), K.transpose(1, 2), V.transpose(1, 2))
+
+
 def test_varlen_and_partial_reject_unsupported(ops):
     from exploring_flash_attention_b200 import FlashAttentionError
     Q = torch.zeros((1, 1, 128, 256), dtype=torch.bfloat16, device="cuda")

@@ -56,14 +56,16 @@ _peer_rings: dict = {}
 
 
 def _peer_ring(shape, dtype, device, group):
-    """Symmetric (peer-mapped) double buffer for the K/V shards + a copy stream, cached per (group, shape, dtype)."""
+    """Peer-mapped staging buffer for this rank's K/V shard ([2,B,H,Ls,d] in symmetric memory), two local receive
+    buffers and two copy streams (K and V travel on separate copy engines); cached per (group, shape, dtype)."""
     import torch.distributed._symmetric_memory as symm_mem
     pg = group if group is not None else dist.group.WORLD
     key = (pg.group_name, tuple(shape), dtype, device.index)
     if key not in _peer_rings:
-        buf = symm_mem.empty((2,) + tuple(shape), dtype=dtype, device=device)
-        hdl = symm_mem.rendezvous(buf, pg)
-        _peer_rings[key] = (buf, hdl, torch.cuda.Stream(device))
+        src = symm_mem.empty((2,) + tuple(shape), dtype=dtype, device=device)
+        hdl = symm_mem.rendezvous(src, pg)
+        recv = torch.empty((2, 2) + tuple(shape), dtype=dtype, device=device)
+        _peer_rings[key] = (src, hdl, (torch.cuda.Stream(device), torch.cuda.Stream(device)), recv)
     return _peer_rings[key]
 
 
@@ -105,9 +107,10 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
 
     transport "nccl": send/recv pairs on the communicator's stream (works on any backend; its kernels need SMs, so
       under the persistent attention kernel the hop is mostly exposed: 10.9 ms at L=16384 on 8 GPUs).
-    transport "peer": every rank PULLS the next shard out of its left neighbour's symmetric-memory buffer with a
-      copy-engine transfer over NVLink on a side stream — no SMs involved, the hop hides under the partial kernel
-      (4.94 ms for the same problem, 1.3 % above the kernels alone).
+    transport "peer": every shard is staged once in its owner's symmetric memory and every rank PULLS the shard it
+      needs next straight from the owner with copy-engine transfers over NVLink/NVSwitch on side streams — no SMs
+      involved, the transfer hides under the partial kernel (4.94 ms for the same problem, 1.3 % above the kernels
+      alone).
     transport "auto" (default): "peer" for CUDA tensors, "nccl" otherwise.
 
     partial_fn / combine_fn default to the CUDA kernels (ops.flash_attention_partial, ops.flash_attention_v2_combine);
@@ -146,28 +149,39 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
             lse_parts[s][:, :C].fill_(float("-inf"))        # weight exp(-inf) = 0 in the merge
 
     if transport == "peer" and world > 1:
-        buf, hdl, copy_stream = _peer_ring((2, B, H, Ls, d), Q.dtype, Q.device, group)
+        # NVSwitch gives every GPU full bandwidth to every peer, so nothing is forwarded: each shard is staged once in
+        # its owner's symmetric memory and at step s rank r pulls the shard of rank (r - s) mod N straight from there
+        # (at any step the N pulls form a permutation: one reader per source).
+        src, hdl, streams, recv = _peer_ring((B, H, Ls, d), Q.dtype, Q.device, group)
         main = torch.cuda.current_stream(Q.device)
-        left = (rank - 1) % world
-        cur = 0
-        buf[0, 0].copy_(K)
-        buf[0, 1].copy_(V)
+        src[0].copy_(K)
+        src[1].copy_(V)
+        hdl.barrier(channel=0)                  # every shard is staged (and every rank has left the previous call)
+
+        def pull(s):
+            peer = hdl.get_buffer((rank - s) % world, src.shape, src.dtype)
+            events = []
+            for t, st in enumerate(streams):
+                st.wait_stream(main)            # the kernel of step s-2, last reader of recv[s % 2], is already enqueued
+                with torch.cuda.stream(st):
+                    recv[s % 2, t].copy_(peer[t], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    events.append(ev)
+            return events
+
+        pending = pull(1)
         for s in range(world):
-            arrived = None
-            if s + 1 < world:
-                copy_stream.wait_stream(main)   # my step s-1 kernel (last reader of buf[1-cur]) and the staging copies
-                with torch.cuda.stream(copy_stream):
-                    # after this barrier every rank's buf[cur] is complete and nobody still pulls from a buf[1-cur]
-                    hdl.barrier(channel=0)
-                    src = hdl.get_buffer(left, buf[cur].shape, buf.dtype, storage_offset=cur * buf[0].numel())
-                    buf[1 - cur].copy_(src, non_blocking=True)
-                    arrived = torch.cuda.Event()
-                    arrived.record(copy_stream)
-            step(s, buf[cur, 0], buf[cur, 1])
-            if arrived is not None:
-                main.wait_event(arrived)
-                cur = 1 - cur
-        hdl.barrier(channel=1)                  # no rank restages buf[0] while a neighbour still pulls from it
+            if s == 0:
+                k, v = K, V
+            else:
+                for ev in pending:
+                    main.wait_event(ev)
+                k, v = recv[s % 2, 0], recv[s % 2, 1]
+                if s + 1 < world:
+                    pending = pull(s + 1)       # travels while the kernel of step s runs
+            step(s, k, v)
+        hdl.barrier(channel=1)                  # nobody restages its shard while a peer may still be pulling it
         return combine_fn(o_parts, lse_parts, Q.dtype, (B, H, Ls, d))
 
     kv = torch.stack([K, V]).contiguous()          # one message per hop: [2,B,H,Ls,d]

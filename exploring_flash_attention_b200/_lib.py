@@ -24,6 +24,7 @@ SYMBOLS = {
     "fa_v1_forward_varlen": (c_int, [c_void_p] * 6 + [c_int] * 6 + [ctypes.c_uint, c_void_p]),
     "fa_partial_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [ctypes.c_longlong] * 3 + [ctypes.c_uint, c_void_p]),
     "fa_v1_tiled_d_forward": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "fa_v1_tiled_d_pair_forward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "fa_v2_num_splits": (c_int, [c_int, c_int]),
     "fa_v2_workspace_bytes": (c_size_t, [c_int] * 5),
     "fa_v2_splitkv_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),

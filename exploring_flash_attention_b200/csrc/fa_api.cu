@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -15,7 +16,12 @@
 #include "../../include/fa_b200.h"
 #include "fa_combine_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_tiled_d_pair_sm100.cuh"
 #include "fa_tiled_d_sm100.cuh"
+
+#ifndef FA_TILED_D_PAIR_DEFAULT
+#define FA_TILED_D_PAIR_DEFAULT 0   // until the CTA-pair kernel has a green parity run on a B200 the slab kernel ships
+#endif
 
 namespace {
 
@@ -210,8 +216,50 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
   return FA_OK;
 }
 
+// K2P: one CTA pair per 128-row q-tile (fa_tiled_d_pair_sm100.cuh).
+template <int D, int DT>
+int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream) {
+  using T = fa::TiledDPairTraits<D, DT>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 64)) != FA_OK) return rc;    // each CTA: its 64 query rows
+  if ((rc = make_map(&tmK, K, DT, D, L, BH, 64)) != FA_OK) return rc;    // each CTA: its 64 keys of a tile
+  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
+  if ((rc = make_map(&tmO, O, DT, D, L, BH, 64)) != FA_OK) return rc;
+  fa::FwdParams p{};
+  p.L = L;
+  p.Lk = L;
+  p.BH = BH;
+  p.kv_per_split = L;
+  p.n_splits = 1;
+  p.scale = 1.0f / std::sqrt(float(D));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  auto kern = fa::fa_tiled_d_pair_kernel<D, DT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  const long long blocks = 2LL * ((L + 127) / 128) * BH;   // the kernel carries __cluster_dims__(2, 1, 1)
+  if (blocks > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-tile) CTA pairs");
+  kern<<<dim3((unsigned)blocks), T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+// Which kernel serves 16-bit d = 512 / 256: FA_B200_TILED_D_PAIR=1 selects the CTA-pair kernel for d = 512,
+// =2 for d = 256 as well, =0 the single-CTA slab kernel.  Read once per process.
+int tiled_d_pair_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("FA_B200_TILED_D_PAIR");
+    return e ? std::atoi(e) : FA_TILED_D_PAIR_DEFAULT;
+  }();
+  return mode;
+}
+
 int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
                      cudaStream_t s) {
+  const int pair_mode = tiled_d_pair_mode();
+  if (pair_mode >= 1 && d == 512 && dtype == fa::DT_BF16) return launch_tiled_d_pair<512, fa::DT_BF16>(Q, K, V, O, BH, L, s);
+  if (pair_mode >= 1 && d == 512 && dtype == fa::DT_F16) return launch_tiled_d_pair<512, fa::DT_F16>(Q, K, V, O, BH, L, s);
+  if (pair_mode >= 2 && d == 256 && dtype == fa::DT_BF16) return launch_tiled_d_pair<256, fa::DT_BF16>(Q, K, V, O, BH, L, s);
+  if (pair_mode >= 2 && d == 256 && dtype == fa::DT_F16) return launch_tiled_d_pair<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
   if (d == 256 && dtype == fa::DT_BF16) return launch_tiled_d<256, fa::DT_BF16>(Q, K, V, O, BH, L, s);
   if (d == 512 && dtype == fa::DT_BF16) return launch_tiled_d<512, fa::DT_BF16>(Q, K, V, O, BH, L, s);
   if (d == 256 && dtype == fa::DT_F16) return launch_tiled_d<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
@@ -344,6 +392,19 @@ int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, 
   if (d <= 128 && !(dtype == FA_DTYPE_F32 && d > 64))
     return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
   return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, s);
+}
+
+int fa_v1_tiled_d_pair_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
+                               int dtype, void* stream) {
+  int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d == 512 && dtype == FA_DTYPE_BF16) return launch_tiled_d_pair<512, fa::DT_BF16>(Q, K, V, O, B * H, L, s);
+  if (d == 512 && dtype == FA_DTYPE_F16) return launch_tiled_d_pair<512, fa::DT_F16>(Q, K, V, O, B * H, L, s);
+  if (d == 256 && dtype == FA_DTYPE_BF16) return launch_tiled_d_pair<256, fa::DT_BF16>(Q, K, V, O, B * H, L, s);
+  if (d == 256 && dtype == FA_DTYPE_F16) return launch_tiled_d_pair<256, fa::DT_F16>(Q, K, V, O, B * H, L, s);
+  return fail(FA_ERR_UNSUPPORTED_D, "the CTA-pair tiled-d kernel serves d in {256,512} for bf16/fp16; got d=" +
+                                        std::to_string(d) + " dtype=" + std::to_string(dtype));
 }
 
 int fa_v2_num_splits(int L, int kv_per_split) {

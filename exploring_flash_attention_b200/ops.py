@@ -173,6 +173,21 @@ def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: i
     return O
 
 
+@_on_device_of
+def flash_attention_v1_tiled_d_pair(Q, K, V, O=None, sync: bool = False):
+    """Tiled-d on CTA pairs (fa_v1_tiled_d_pair_forward): bf16/fp16, d in {256, 512}."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    if O is None:
+        O = torch.empty_like(Q)
+    lib = _lib.load()
+    _lib.check(lib.fa_v1_tiled_d_pair_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d,
+                                              _DTYPES[Q.dtype], _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return O
+
+
 def v2_num_splits(L: int, kv_per_split: int) -> int:
     return _lib.load().fa_v2_num_splits(L, kv_per_split)
 

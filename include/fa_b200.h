@@ -91,6 +91,12 @@ int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opart
 int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
                           int d_tile_qk, int d_tile_v, int dtype, void* stream);
 
+/* The same contract served by the CTA-pair kernel (two SMs share one 128-row query tile through 2-CTA tensor-core
+ * MMAs, so no score tile is computed twice at d = 512): 16-bit dtypes, d in {256, 512}.  fa_v1_tiled_d_forward
+ * routes to it when the environment variable FA_B200_TILED_D_PAIR is 1 (d = 512) or 2 (d = 256 as well). */
+int fa_v1_tiled_d_pair_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
+                               int dtype, void* stream);
+
 /* ---- V2 split-KV ----------------------------------------------------------------------------
  * Replaces  void flash_attention_v2(Q,K,V,O,B,H,L,d,d_tile_qk,d_tile_v,kv_tiles_per_block)
  *           flash_attention_v2/CUDA/flash_attention_v2.h:438-509 (partial_attention_kernel :243-341,

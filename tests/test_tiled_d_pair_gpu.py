@@ -1,0 +1,101 @@
+"""GPU (-m gpu): the CTA-pair tiled-d kernel (fa_v1_tiled_d_pair_forward, csrc/fa_tiled_d_pair_sm100.cuh) against the
+float64 oracle and against the single-CTA slab kernel, through the C ABI.  Same tolerances as test_parity_gpu.py.
+
+Gated: until the pair kernel has had a green run on a B200 these tests only run with FA_B200_TEST_PAIR=1 (the shipped
+default routing, FA_TILED_D_PAIR_DEFAULT in csrc/fa_api.cu, is the slab kernel the main parity suite covers).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FA_B200_TEST_PAIR", "0") != "1",
+                                 reason="CTA-pair tiled-d kernel is opt-in (FA_B200_TEST_PAIR=1)")]
+
+TOL = {torch.bfloat16: 2e-3, torch.float16: 2e-3}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from exploring_flash_attention_b200 import _lib, ops as _ops
+    _lib.load()
+    return _ops
+
+
+def uniform_qkv(B, H, L, d, dtype, seed=42):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return tuple((torch.rand((B, H, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
+
+
+def oracle_out(Q, K, V, heads=None, rows=None):
+    f = lambda x: x.float().cpu().numpy()
+    return reference.naive_attention_batched_f64(f(Q), f(K), f(V), heads=heads, rows=rows)
+
+
+def max_err(O, ref, heads=None, rows=None):
+    L, d = O.shape[-2:]
+    got = O.float().cpu().numpy().reshape(-1, L, d).astype(np.float64)
+    if heads is not None:
+        got = got[list(heads)]
+    if rows is not None:
+        got = got[:, rows]
+    return np.abs(got - ref).max()
+
+
+@pytest.mark.parametrize("B,H,L,d,dtype", [
+    (1, 1, 128, 512, torch.bfloat16), (1, 2, 256, 512, torch.bfloat16), (1, 2, 384, 512, torch.float16),
+    (1, 2, 333, 512, torch.bfloat16), (2, 1, 129, 512, torch.bfloat16), (1, 1, 1, 512, torch.bfloat16),
+    (1, 1, 64, 512, torch.float16), (1, 1, 65, 512, torch.bfloat16), (1, 1, 300, 512, torch.bfloat16),
+    (1, 2, 256, 256, torch.bfloat16), (1, 1, 100, 256, torch.float16), (2, 3, 777, 256, torch.bfloat16),
+    (2, 2, 1024, 512, torch.bfloat16),
+])
+def test_pair_matches_oracle_and_slab_kernel(ops, B, H, L, d, dtype):
+    Q, K, V = uniform_qkv(B, H, L, d, dtype)
+    O = ops.flash_attention_v1_tiled_d_pair(Q, K, V, sync=True)
+    assert not torch.isnan(O).any()
+    assert max_err(O, oracle_out(Q, K, V)) <= TOL[dtype]
+    O_slab = ops.flash_attention_v1_tiled_d(Q, K, V, sync=True)
+    assert (O.float() - O_slab.float()).abs().max().item() <= 2 * TOL[dtype]
+
+
+def test_pair_rescale_path(ops):
+    """Key norms that grow along the sequence force the lazy O rescale (running max moves by more than 2^8)."""
+    B, H, L, d = 1, 1, 640, 512
+    Q, K, V = uniform_qkv(B, H, L, d, torch.bfloat16)
+    ramp = torch.linspace(0.3, 8.0, L, device="cuda").view(1, 1, L, 1)
+    K = (K.float() * ramp).bfloat16()
+    O = ops.flash_attention_v1_tiled_d_pair(Q, K, V, sync=True)
+    ref = oracle_out(Q, K, V)
+    assert not torch.isnan(O).any()
+    assert max_err(O, ref) <= 2e-3 * max(1.0, np.abs(ref).max()) * 4
+
+
+def test_pair_rejects_what_it_does_not_serve(ops):
+    from exploring_flash_attention_b200 import FlashAttentionError
+    Q, K, V = uniform_qkv(1, 1, 64, 128, torch.bfloat16)
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_v1_tiled_d_pair(Q, K, V)
+    Q, K, V = (x.float() for x in uniform_qkv(1, 1, 64, 256, torch.bfloat16))
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_v1_tiled_d_pair(Q, K, V)
+
+
+def test_pair_c5_full_size_sampled(ops):
+    """BASELINE.json configs[4]: B16 H8 L4096 d512 bf16 — sampled oracle rows + rows of P sum to one."""
+    B, H, L, d = 16, 8, 4096, 512
+    g = torch.Generator(device="cpu").manual_seed(42)
+    base = [((torch.rand((1, H, L, d), generator=g) * 2 - 1)).bfloat16().cuda() for _ in range(3)]
+    Q, K, V = (x.expand(B, H, L, d).contiguous() for x in base)
+    Q[1:] = Q[1:].roll(1, dims=2)
+    O = ops.flash_attention_v1_tiled_d_pair(Q, K, V, sync=True)
+    heads = [0, 77, B * H - 1]
+    rows = np.r_[0:32, L // 2:L // 2 + 32, L - 32:L]
+    assert max_err(O, oracle_out(Q, K, V, heads=heads, rows=rows), heads=heads, rows=rows) <= 2e-3
+    ones = torch.ones_like(V)
+    assert (ops.flash_attention_v1_tiled_d_pair(Q, K, ones, sync=True).float() - 1).abs().max().item() <= 4e-3

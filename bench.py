@@ -209,7 +209,7 @@ def run_ours(args):
     achieved = flops(Bl, Hl, L, d) / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0),
                 "unit": "TFLOP/s", "frac": round(achieved / (pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0)), 4),
-                "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "kernel": "fa_fwd_kernel" if d <= 128 else "fa_tiled_d_kernel",
+                "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "kernel": "fa_fwd_kernel" if d <= 128 else ("fa_tiled_d_pair_kernel" if d == 512 and dt != "f32" else "fa_tiled_d_kernel"),
                 "peak_source": pk["source"] + (", burst bf16 cuBLAS" if dt != "f32" else ", burst bf16 cuBLAS / 2 (tf32)"),
                 "frac_of_sustained": round(achieved / (pk["bf16_tflops_sustained"] / (2.0 if dt == "f32" else 1.0)), 4)
                 if pk["bf16_tflops_sustained"] else None,

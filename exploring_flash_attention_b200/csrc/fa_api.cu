@@ -20,7 +20,8 @@
 #include "fa_tiled_d_sm100.cuh"
 
 #ifndef FA_TILED_D_PAIR_DEFAULT
-#define FA_TILED_D_PAIR_DEFAULT 0   // until the CTA-pair kernel has a green parity run on a B200 the slab kernel ships
+#define FA_TILED_D_PAIR_DEFAULT 1   // 1: 16-bit d = 512 runs on CTA pairs (B200: 1036 vs 830 TFLOP/s for the slab kernel at
+                                    // B16 H8 L4096); d = 256 stays on the slab kernel (1340 vs 680)
 #endif
 
 namespace {

@@ -8,22 +8,39 @@
 // 256-wide slab of O and both slabs recompute S (1.5x the algorithmic MMA work).  Here the two SMs of a pair share one
 // 128-row Q tile BY ROWS: with a 2-CTA MMA of M = 128 each SM computes 64 rows at full tensor rate, and its 64 x N
 // block of D is spread over all 128 TMEM lanes with N/2 columns (lane r: columns [0,N/2), lane 64+r: [N/2,N)).
-//   TMEM per CTA   S[0] [0,64)  S[1] [64,128)  O [128, 128 + D/2)           (d = 512: 384 of 512 columns)
+//   TMEM per CTA   S[b] [64b, 64b+64) for b < NB,  O [64 NB, 64 NB + D/2)     (d = 512, NB = 4: all 512 columns)
 //   MMAs (leader)  S = Q K^T : M128 N128 K16, A = Q rows of each CTA, B = K tile, keys [0,64) from the leader's smem and
 //                  [64,128) from the peer's;   O[:, 128g .. 128g+127] += P V : A = P (smem, written by each CTA's own
 //                  softmax warps), B = V columns 128g + 64*rank + [0,64) from each CTA.  No S is computed twice and
 //                  every K / V byte is loaded by exactly one of the two SMs.
-//   smem per CTA   Q 64 rows x D (resident), P 2 x [64 rows x 128 keys], ring of 16 KB stages: a K stage = two d-chunks
+//   smem per CTA   Q 64 rows x D (resident), P NB x [64 rows x 128 keys], ring of 16 KB stages: a K stage = two d-chunks
 //                  [64 keys x 64 d], a V stage = [128 keys x 64 d].
 //   warps          0-3 softmax (thread t <-> TMEM lane t: row t & 63, key half t >> 6; the two threads of a row
 //                  exchange their half-row max through smem), 4 TMA producer (both CTAs), 5 MMA issuer (leader only).
 //   barriers       full[] / q_full / p_full[] live in the leader (the peer's TMA and softmax threads signal them
-//                  remotely); empty[] / s_full[] / pv_done are signalled in both CTAs by multicast tcgen05.commit.
+//                  remotely); empty[] / s_full[] / pv_done[] are signalled in both CTAs by multicast tcgen05.commit.
+//   schedule       S and P are NB-deep (TMEM and smem have the room), and the leader issues QK(j+NB-1) BEFORE it waits
+//                  for P(j): the tensor pipe always has a score tile queued while the softmax of the oldest tile and
+//                  the cross-SM barrier hops complete.  Issue order  QK(0..NB-2) | QK(j+NB-1) PV(j) | ...
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "fa_fwd_sm100.cuh"
+
+#ifndef FA_PAIR_NB
+#define FA_PAIR_NB 4            // depth of the S (TMEM) and P (smem) buffers: 2, 3 or 4 (B200, B16 H8 L4096 d512: 1005 /
+                                // 1010 / 1036 TFLOP/s)
+#endif
+#ifndef FA_PAIR_WARP_ARRIVE
+#define FA_PAIR_WARP_ARRIVE 0   // 1: one p_full arrival per softmax warp instead of one per thread
+#endif
+#ifndef FA_PAIR_PROBE
+#define FA_PAIR_PROBE 0         // timing probes that BREAK the numerics: 1 no half-row max exchange, 2 no exponentials,
+#endif                          // 4 no P stores (never ship non-zero)
+#ifndef FA_PAIR_FULL_FENCE
+#define FA_PAIR_FULL_FENCE 0    // 1: fence.proxy.async over every state space instead of shared::cta
+#endif
 
 namespace fa {
 
@@ -43,15 +60,19 @@ struct TiledDPairTraits {
   static constexpr int VST = NG;                    // V stages per KV tile
   static constexpr int Q_BYTES = NKC * HALF_BLK;
   static constexpr int P_BYTES = 2 * HALF_BLK;      // [64 rows x 128 keys] 16-bit
+  static constexpr int NB = FA_PAIR_NB;             // S / P buffers
+  static_assert(NB >= 2 && NB <= 4, "FA_PAIR_NB must be 2, 3 or 4");
   static constexpr int MISC_BYTES = 2048;           // barriers, TMEM slot, row-max / row-sum exchange
-  static constexpr int NS = (227 * 1024 - 1024 - MISC_BYTES - Q_BYTES - 2 * P_BYTES) / STAGE_BYTES;  // 8 (d=512), 10
-  static constexpr int NUM_BARS = 1 + 2 * NS + 2 + 2 + 1;
+  static constexpr int NS = (227 * 1024 - 1024 - MISC_BYTES - Q_BYTES - NB * P_BYTES) / STAGE_BYTES;  // d=512, NB=4: 6
+  static constexpr int NUM_BARS = 1 + 2 * NS + 3 * NB;
   static_assert(NUM_BARS * 8 + 16 + 3 * 128 * 4 <= MISC_BYTES, "misc area too small");
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + 2 * P_BYTES + NS * STAGE_BYTES + MISC_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + NB * P_BYTES + NS * STAGE_BYTES + MISC_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr int THREADS = 192;
-  static constexpr int TM_S = 0, TM_O = 128;
-  static constexpr int TMEM_COLS = (128 + NG * 64 <= 256) ? 256 : 512;
+  static constexpr int TM_S = 0, TM_O = NB * 64;
+  static_assert(TM_O + NG * 64 <= 512, "S buffers and O must fit TMEM");
+  static constexpr int TMEM_COLS = (TM_O + NG * 64 <= 256) ? 256 : 512;
+  static constexpr int P_ARRIVALS = FA_PAIR_WARP_ARRIVE ? 8 : 256;   // both CTAs' softmax warps / threads
 };
 
 template <int D, int DT>
@@ -61,21 +82,21 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        const FwdParams p) {
   using T = TiledDPairTraits<D, DT>;
   constexpr int BN = T::BN, CH = T::CH, HALF_BLK = T::HALF_BLK, STAGE_BYTES = T::STAGE_BYTES, NKC = T::NKC, NG = T::NG,
-                NS = T::NS, KST = T::KST;
+                NS = T::NS, KST = T::KST, NB = T::NB;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // NKC blocks [64 rows x 128 B]; reused as the O staging area
-  uint8_t* sP = sQ + T::Q_BYTES;                        // 2 buffers x 2 blocks [64 rows x 64 keys]
-  uint8_t* sRing = sP + 2 * T::P_BYTES;
+  uint8_t* sP = sQ + T::Q_BYTES;                        // NB buffers x 2 blocks [64 rows x 64 keys]
+  uint8_t* sRing = sP + NB * T::P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NS * STAGE_BYTES);
   uint64_t* q_full = bars;            // [1]  leader: both CTAs' Q blocks landed
   uint64_t* full = q_full + 1;        // [NS] leader: both CTAs' halves of a stage landed
   uint64_t* empty = full + NS;        // [NS] both:   MMAs that read the stage retired (multicast commit)
-  uint64_t* s_full = empty + NS;      // [2]  both:   S[b] holds tile j (multicast commit)
-  uint64_t* p_full = s_full + 2;      // [2]  leader: 2 x 128 softmax threads wrote P[b] (and rescaled O)
-  uint64_t* pv_done = p_full + 2;     // [1]  both:   PV(j) retired (phase j)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_full = empty + NS;      // [NB] both:   S[b] holds tile j, b = j % NB (multicast commit)
+  uint64_t* p_full = s_full + NB;     // [NB] leader: both CTAs' softmax warps wrote P[b] (and rescaled O)
+  uint64_t* pv_done = p_full + NB;    // [NB] both:   PV(j) retired (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NB);
   float* mx_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + T::NUM_BARS * 8 + 16);  // [2][128]
   float* l_buf = mx_buf + 256;                                                                          // [128]
 
@@ -88,6 +109,8 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int q_row0 = (pair % n_qtiles) * T::BM + int(rank) * T::BMC;   // first query row of THIS CTA
   const int bh = pair / n_qtiles;
   const int n_tiles = (p.L + BN - 1) / BN;
+  // (Tried and dropped: starting each q-tile's KV loop at a different tile so the q-tiles of a head do not pull the same
+  //  K/V lines out of L2 at the same time — no measurable change, 1031 vs 1039 TFLOP/s at B16 H8 L4096 d512.)
 
   if (warp == 5 && lane == 0) {
     mbar_init(q_full, 1);
@@ -95,11 +118,11 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NB; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 256);
+      mbar_init(&p_full[b], T::P_ARRIVALS);
+      mbar_init(&pv_done[b], 1);
     }
-    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 4) {
@@ -149,10 +172,10 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tma_load_3d_pair(sRing + stage * STAGE_BYTES, &tmV, bar, g * 128 + int(rank) * 64, j * BN, bh);
         }
       };
-      // consumption order: K(0) | K(1) V(0) | K(2) V(1) | ... | V(n-1)
-      load_k(0);
+      // consumption order: K(0) .. K(NB-2) | K(NB-1) V(0) | K(NB) V(1) | ... | V(n-1)
+      for (int j = 0; j < NB - 1 && j < n_tiles; ++j) load_k(j);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) load_k(j + 1);
+        if (j + NB - 1 < n_tiles) load_k(j + NB - 1);
         load_v(j);
       }
     }
@@ -197,17 +220,22 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tc_commit_pair(&empty[stage], 3);
           ++it;
         }
-        tc_commit_pair(pv_done, 3);
+        tc_commit_pair(&pv_done[b], 3);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
-      qk(0);
+      for (int j = 0; j < NB - 1 && j < n_tiles; ++j) qk(j);
+      int b = 0, b_ahead = NB - 1;   // j % NB, (j + NB - 1) % NB
+      uint32_t par = 0;              // (j / NB) & 1
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) qk((j + 1) & 1);   // overlaps softmax(j); issued after PV(j-1), whose p_full wait proved
-                                                // that both CTAs' softmax(j-1) had read S[(j+1)&1]
-        mbar_wait_cluster(&p_full[j & 1], (j >> 1) & 1);
+        // QK(j+NB-1) goes in BEFORE the wait for P(j).  Its S buffer held tile j-1, which both CTAs' softmax had read
+        // when they signalled p_full(j-1) (waited for one iteration ago).
+        if (j + NB - 1 < n_tiles) qk(b_ahead);
+        mbar_wait_cluster(&p_full[b], par);
         tc_fence_after();
-        pv(j & 1, j > 0 ? 1u : 0u);
+        pv(b, j > 0 ? 1u : 0u);
+        if (++b == NB) { b = 0; par ^= 1u; }
+        if (++b_ahead == NB) b_ahead = 0;
       }
     }
   } else {
@@ -222,10 +250,12 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float m_used = -CUDART_INF_F;
     float l = 0.f;
 
+    int b = 0, b_prev = NB - 1;        // j % NB, (j - 1) % NB
+    uint32_t par = 0, par_prev = 1;    // (j / NB) & 1, ((j - 1) / NB) & 1
     for (int j = 0; j < n_tiles; ++j) {
-      const int b = j & 1;
       const uint32_t tS = t_lane + T::TM_S + b * 64;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+      // S[b] ready; in-order completion also proves PV(j-NB) retired, i.e. P[b] may be overwritten.
+      mbar_wait(&s_full[b], par);
       tc_fence_after();
       uint32_t s[2][32];
       tmem_ld32(tS, s[0]);
@@ -248,17 +278,22 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       // the other half of this row lives in thread t ^ 64: exchange the half-row maxima (key 0 of a tile always exists,
       // so the joint maximum is finite)
-      mx_buf[b * 128 + t] = fmaxf(mx0, mx1);
+#if FA_PAIR_PROBE & 1
+      const float mx = fmaxf(mx0, mx1);
+#else
+      mx_buf[(j & 1) * 128 + t] = fmaxf(mx0, mx1);
       named_bar_sync(1, 128);
-      const float mx = fmaxf(fmaxf(mx0, mx1), mx_buf[b * 128 + (t ^ 64)]);
+      const float mx = fmaxf(fmaxf(mx0, mx1), mx_buf[(j & 1) * 128 + (t ^ 64)]);
+#endif
 
       if (j == 0) {
         m_used = mx;
       } else {
         const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          // PV(j-1) was issued after QK(j): wait for its own commit (phase j-1) before touching O.
-          mbar_wait(pv_done, (j - 1) & 1);
+          // O may only be touched once PV(j-1) has retired.  Its barrier last completed for tile j-1-NB (proved by
+          // S(j) being ready) and cannot complete again before this thread signals P(j): the parity is unambiguous.
+          mbar_wait(&pv_done[b_prev], par_prev);
           tc_fence_after();
           const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
           if (need) m_used = mx;
@@ -280,8 +315,13 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int x = 0; x < 32; ++x) {
+#if FA_PAIR_PROBE & 2
+        const float p0 = fmaf(__uint_as_float(s[0][x]), p.scale_log2, neg_m);
+        const float p1 = fmaf(__uint_as_float(s[1][x]), p.scale_log2, neg_m);
+#else
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[0][x]), p.scale_log2, neg_m));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[1][x]), p.scale_log2, neg_m));
+#endif
         l0 += p0;
         l1 += p1;
         s[0][x] = __float_as_uint(p0);
@@ -302,21 +342,35 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         v.y = pk2(2);
         v.z = pk2(4);
         v.w = pk2(6);
+#if FA_PAIR_PROBE & 4
+        if (v.x == 0x12345678u) st_shared_v4(p_row + ((q ^ (row & 7)) << 4), v);
+#else
         st_shared_v4(p_row + ((q ^ (row & 7)) << 4), v);
+#endif
       }
-      fence_proxy_async_all();   // st.shared -> readable by the tensor cores of both SMs
-      // Every thread steps through every phase of pv_done in order (PV(j-1) runs under this tile's softmax and QK(j+1)
-      // is queued behind it, so this costs nothing): a parity wait can then never be two phases behind.
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+      // st.shared -> visible to the tensor core (P is the A operand: only this SM reads it)
+#if FA_PAIR_FULL_FENCE
+      fence_proxy_async_all();
+#else
+      fence_proxy_async_smem();
+#endif
       tc_fence_before();
+#if FA_PAIR_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(p_full_ld + b * 8);
+#else
       mbar_arrive_cluster(p_full_ld + b * 8);
+#endif
+      b_prev = b;
+      par_prev = par;
+      if (++b == NB) { b = 0; par ^= 1u; }
     }
 
     // ------------------------------- epilogue: O / l -> 16-bit -> smem (Q's dead blocks) -> TMA store ------------
     l_buf[t] = l;
     named_bar_sync(1, 128);
     const float inv_l = 1.0f / (l + l_buf[t ^ 64]);
-    mbar_wait(pv_done, (n_tiles - 1) & 1);   // phases 0 .. n-2 were stepped through in the loop
+    mbar_wait(&pv_done[b_prev], par_prev);   // the last PV (same parity argument as in the rescale branch)
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < NG * 2; ++c) {   // 32 columns at a time; group g = c >> 1 holds d = 128g + 64*half + [0,64)

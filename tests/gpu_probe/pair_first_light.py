@@ -2,6 +2,7 @@
 
     python tests/gpu_probe/pair_first_light.py            # every case, each in its own subprocess with a timeout
     python tests/gpu_probe/pair_first_light.py --case N   # one case in this process
+    FA_B200_LIB=build_variants/x.so python tests/gpu_probe/pair_first_light.py --cases 1,5,6   # A/B of a tuning build
 
 A case prints one JSON line: max-abs error of both kernels vs float64, the error of the pair kernel by 32-row block
 and 64-column block (a layout bug shows up as a block pattern), and CUDA-event timings.
@@ -74,6 +75,9 @@ def run_case(i: int) -> None:
 if __name__ == "__main__":
     if "--case" in sys.argv:
         run_case(int(sys.argv[sys.argv.index("--case") + 1]))
+    elif "--cases" in sys.argv:      # several cases in this process (A/B of builds selected through FA_B200_LIB)
+        for i in sys.argv[sys.argv.index("--cases") + 1].split(","):
+            run_case(int(i))
     else:
         for i in range(len(CASES)):
             try:

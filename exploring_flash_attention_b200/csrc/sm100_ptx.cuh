@@ -238,24 +238,17 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-// arrive (count 1) on an mbarrier of any CTA in the cluster; releases this thread's earlier writes at cluster scope
+// Arrive (count 1) on an mbarrier of any CTA in the cluster.  Deliberately the plain form: with `.release.cluster` ptxas
+// emits MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive (and CCTL.IVALL behind every `.acquire.cluster`
+// wait), which put ~1 us on the softmax -> MMA hop of the CTA-pair kernels (dense d=128 on pairs: 804 TFLOP/s with the
+// fences).  What crosses the barrier here is never plain memory: P / O live in TMEM, ordered by
+// tcgen05.wait + tcgen05.fence::before/after_thread_sync, or in shared memory read by the tensor core, ordered by
+// fence.proxy.async before the arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > FA_SPIN_LIMIT) __trap();
-  } while (!ok);
-}
+// wait on a local mbarrier whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // generic-proxy writes -> visible to the async proxy in every state space (a peer SM's tensor core reads this CTA's smem)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 

@@ -1,6 +1,6 @@
-"""A/B of the dense d=128 forward on CTA pairs (K1P, FA_B200_FWD_PAIR=1) against the single-CTA kernel (K1, =0).
+"""A/B of the dense d=128 forward on CTA pairs (K1P, FA_B200_FWD_PAIR=1; K1Q, =2) against the single-CTA kernel (K1, =0).
 
-    python tests/gpu_probe/fwd_pair_ab.py            # modes 0, 1, 0 in subprocesses (the variable is read once per process)
+    python tests/gpu_probe/fwd_pair_ab.py [--modes 2,0]   # default modes 0, 1, 0, each in a subprocess (the variable is read once)
     python tests/gpu_probe/fwd_pair_ab.py --run      # the cases in this process, with whatever FA_B200_FWD_PAIR says
 
 Each case: max-abs error against float64 on sampled heads/rows; the big ones are also timed with CUDA events.
@@ -74,7 +74,8 @@ if __name__ == "__main__":
     if "--run" in sys.argv:
         run()
     else:
-        for mode in ("0", "1", "0"):
+        modes = sys.argv[sys.argv.index("--modes") + 1].split(",") if "--modes" in sys.argv else ("0", "1", "0")
+        for mode in modes:
             env = dict(os.environ, FA_B200_FWD_PAIR=mode)
             try:
                 r = subprocess.run([sys.executable, __file__, "--run"], capture_output=True, text=True, env=env, timeout=150)

@@ -1,7 +1,8 @@
-"""GPU (-m gpu): K1P, the dense d = 128 forward on CTA pairs (csrc/fa_fwd_pair_sm100.cuh), against the float64 oracle
-and against K1 through the reference-shaped entry points.  K1P is selected per process (FA_B200_FWD_PAIR=1, read once;
-the compiled default is FA_FWD_PAIR_DEFAULT in csrc/fa_api.cu), so the check runs in a subprocess; whatever needs
-masks, lengths or a split must keep going to K1 in the same process.  Tolerance: 2e-3 (bf16 / fp16, BASELINE.json).
+"""GPU (-m gpu): the dense d = 128 forward on CTA pairs — K1P (csrc/fa_fwd_pair_sm100.cuh, FA_B200_FWD_PAIR=1) and the
+experimental K1Q (csrc/fa_fwd_pair2_sm100.cuh, =2) — against the float64 oracle through the reference-shaped entry
+points, next to K1 (=0).  The variable is read once per process (compiled default: FA_FWD_PAIR_DEFAULT in
+csrc/fa_api.cu), so each check runs in a subprocess; whatever needs masks, lengths or a split must keep going to K1 in
+the same process.  Tolerance: 2e-3 (bf16 / fp16, BASELINE.json).
 """
 import os
 import subprocess
@@ -47,7 +48,7 @@ assert worst <= 2e-3, worst
 """
 
 
-@pytest.mark.parametrize("mode", ["1", "0"])
+@pytest.mark.parametrize("mode", ["1", "2", "0"])
 def test_dense_d128_forward_on_cta_pairs(mode):
     if not torch.cuda.is_available():
         pytest.fail("GPU tests need a CUDA device")

@@ -12,10 +12,12 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 #include "../../include/fa_b200.h"
 #include "fa_combine_sm100.cuh"
 #include "fa_fwd_pair2_sm100.cuh"
+#include "fa_fwd_pair4_sm100.cuh"
 #include "fa_fwd_pair_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_tiled_d_pair_sm100.cuh"
@@ -124,7 +126,8 @@ struct FwdExtra {
 };
 
 // K1P: dense d = 128 forward on CTA pairs (both SMs of a pair share every K / V tile through 2-CTA MMAs).
-// FA_B200_FWD_PAIR = 0 / 1 / 2 overrides the compiled default (read once per process); 2 = the experimental K1Q.
+// FA_B200_FWD_PAIR = 0 / 1 / 2 / 3 overrides the compiled default (read once per process); 2 = the experimental K1Q,
+// 3 = K1R (K1Q with four softmax warpgroups; UNVERIFIED on a GPU, see fa_fwd_pair4_sm100.cuh).
 int fwd_pair_mode() {
   static const int mode = [] {
     const char* e = std::getenv("FA_B200_FWD_PAIR");
@@ -170,10 +173,10 @@ int launch_fwd_pair(const void* Q, const void* K, const void* V, void* O, int BH
 }
 
 // K1Q (experimental, FA_B200_FWD_PAIR=2): one Q tile per CTA of a pair, S and P double-buffered (fa_fwd_pair2_sm100.cuh).
-template <int DT>
+template <int DT, bool FOUR_WG>
 int launch_fwd_pair2(const void* Q, const void* K, const void* V, void* O, int BH, int L, float* lse_out,
                      cudaStream_t stream) {
-  using T = fa::FwdPair2Traits<DT>;
+  using T = std::conditional_t<FOUR_WG, fa::FwdPair4Traits<DT>, fa::FwdPair2Traits<DT>>;
   constexpr int D = 128;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
@@ -195,7 +198,7 @@ int launch_fwd_pair2(const void* Q, const void* K, const void* V, void* O, int B
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.lse_out = lse_out;
   p.out_head_rows = L;
-  auto kern = fa::fa_fwd_pair2_kernel<DT>;
+  auto kern = FOUR_WG ? fa::fa_fwd_pair4_kernel<DT> : fa::fa_fwd_pair2_kernel<DT>;   // K1R (unverified) / K1Q
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   const int sms = sm_count();
   if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
@@ -212,8 +215,9 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   if constexpr (!SPLIT && D == 128 && DT != fa::DT_F32) {
     if (fwd_pair_mode() >= 1 && !causal && ex.kv_lens == nullptr && (ex.Lk == 0 || ex.Lk == L) && ex.q_head_rows == 0 &&
         ex.kv_head_rows == 0 && ex.out_head_rows == 0)
-      return fwd_pair_mode() == 2 ? launch_fwd_pair2<DT>(Q, K, V, O, BH, L, lse_out, stream)
-                                  : launch_fwd_pair<DT>(Q, K, V, O, BH, L, lse_out, stream);
+      return fwd_pair_mode() == 3   ? launch_fwd_pair2<DT, true>(Q, K, V, O, BH, L, lse_out, stream)
+             : fwd_pair_mode() == 2 ? launch_fwd_pair2<DT, false>(Q, K, V, O, BH, L, lse_out, stream)
+                                    : launch_fwd_pair<DT>(Q, K, V, O, BH, L, lse_out, stream);
   }
   using T = fa::FwdTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;

@@ -1,4 +1,8 @@
-"""First light / A-B of the CTA-pair tiled-d kernel (fa_v1_tiled_d_pair_forward) against the slab kernel and float64.
+"""First light / A-B of the CTA-pair tiled-d kernel (fa_v1_tiled_d_pair_forward) against the routed tiled-d entry point
+(fa_v1_tiled_d_forward) and float64.  The routed call is the single-CTA slab kernel K2 for d = 256 and, when the process runs
+with FA_B200_TILED_D_PAIR=0, for d = 512 as well; otherwise d = 512 is the pair kernel on both sides and the two timings only
+show the drift between a first and a second timing loop (power cap).  JSON keys keep the historical "slab_" prefix for the
+routed call.
 
     python tests/gpu_probe/pair_first_light.py            # every case, each in its own subprocess with a timeout
     python tests/gpu_probe/pair_first_light.py --case N   # one case in this process

@@ -262,8 +262,8 @@ NCU_TRAFFIC_BYTES: dict = {"c2": 243_684_096}   # profiles/r1_fwd_c2_persistent_
 
 
 def side_measurements(torch, ops, pk):
-    """Other BASELINE.json configs, reported beside the headline (not the bench value): C4 long sequence, C1 tf32,
-    C3 split-KV + combine with the combine kernel's HBM roofline."""
+    """Other BASELINE.json configs, reported beside the headline (not the bench value): C4 long sequence, C5 d=512,
+    C1 tf32, C3 split-KV + combine with the combine kernel's HBM roofline."""
     res = {}
 
     def timed(fn, n, warm=3):
@@ -293,6 +293,19 @@ def side_measurements(torch, ops, pk):
         del q, k, v, o
     except Exception as e:  # noqa: BLE001
         res["c4_error"] = str(e)[:200]
+    try:
+        B, H, L, d = 16, 8, 4096, 512                      # configs[4]: tiled-d on CTA pairs (fa_tiled_d_pair_kernel)
+        q, k, v = mk(1, H, L, d, torch.bfloat16)
+        q, k, v = (x.expand(B, H, L, d).contiguous() for x in (q, k, v))
+        o = torch.empty_like(q)
+        ms = timed(lambda: ops.flash_attention_v1_tiled_d(q, k, v, o), 5, warm=2)
+        tf = flops(B, H, L, d) / (ms * 1e-3) / 1e12
+        res["c5_B16_H8_L4096_d512_bf16"] = {"ms": round(ms, 3), "tflops": round(tf, 1),
+                                           "frac_of_measured_bf16_peak": round(tf / pk["bf16_tflops"], 4),
+                                           "bound": "shared-memory bandwidth / L2 delivery (DESIGN.md K2P)"}
+        del q, k, v, o
+    except Exception as e:  # noqa: BLE001
+        res["c5_error"] = str(e)[:200]
     try:
         B, H, L, d = 32, 8, 1024, 32
         q, k, v = mk(B, H, L, d, torch.float32)

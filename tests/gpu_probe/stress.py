@@ -21,7 +21,7 @@ while time.time() < t_end:
     if d >= 256:
         L = min(L, 1024)
     BH = rng.choice([1, 2, 3, 5, 37, 149, 300]) if L <= 300 else rng.choice([1, 2, 3, 5, 19])
-    variant = rng.choice(["v1", "v1", "v2", "varlen", "causal", "parts"]) if d <= 128 else "td"
+    variant = rng.choice(["v1", "v1", "v2", "varlen", "causal", "parts"]) if d <= 128 else rng.choice(["td", "tdp"])
     g = torch.Generator().manual_seed(n)
     Q, K, V = ((torch.rand((1, BH, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
     mask = None          # [BH, Lq, Lk] bool of attended keys, when the variant masks
@@ -56,6 +56,9 @@ while time.time() < t_end:
     elif variant == "td":
         O = ops.flash_attention_v1_tiled_d(Q, K, V, sync=True)
         tag = "td"
+    elif variant == "tdp":     # the CTA-pair kernel called explicitly (it also serves d = 256, which "td" routes to K2)
+        O = ops.flash_attention_v1_tiled_d_pair(Q, K, V, sync=True)
+        tag = "tdp"
     else:
         kvs = rng.choice([8, 64, 100, 128, 256, 1000])
         O = ops.flash_attention_v2(Q, K, V, kvs, sync=True)

@@ -395,12 +395,48 @@ def cpu_baseline(workload):
         heads = int(os.environ.get("FA_BENCH_CPU_HEADS", heads))   # test hook: shrink the CPU sample
         secs, kind, threads = cpu_sample(workload, heads, threads)
         tf = flops(1, heads, L, d) / secs / 1e12
-        return {"value": round(tf, 5), "unit": UNIT, "cores": threads, "kind": kind,
-                "sample": f"{heads} of {B * H} heads of the same shape (L={L}, d={d}, fp16 storage like the reference's "
-                          f"DATA_TYPE=__half), 1 pass, {secs:.1f} s",
-                "seconds": round(secs, 2), "extrapolated_full_batch_seconds": round(secs * B * H / heads, 1)}
+        out = {"value": round(tf, 5), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{heads} of {B * H} heads of the same shape (L={L}, d={d}, fp16 storage like the reference's "
+                         f"DATA_TYPE=__half), 1 pass, {secs:.1f} s",
+               "seconds": round(secs, 2), "extrapolated_full_batch_seconds": round(secs * B * H / heads, 1)}
+        out["also"] = cpu_python_paths(B * H, L, d)
+        return out
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+
+def cpu_python_paths(n_heads, L, d):
+    """The reference's two Python CPU paths on small stated samples of the same shape: its oracle
+    naive_attention (common/reference.py:7-21; BLAS matmuls, all host threads) looped over heads, and the V1 tile loop
+    of numpy_gpu_like_opt2.py:198-241 with the reference's default Bq = Bk = 8 (restated per tile in NumPy, so this port
+    is far faster than the reference's per-element Python loops: 11 s per head at L=1024, d=32)."""
+    res = {}
+    try:
+        import numpy as np
+        from oracle import reference, tiled
+        rng = np.random.default_rng(0)
+        # bounded samples: ~0.3 TFLOP of BLAS work for the oracle, one head for the tile loop if it has <= 32k tile updates
+        heads = max(1, min(n_heads, 32, int(0.3e12 / flops(1, 1, L, d))))
+        heads = int(os.environ.get("FA_BENCH_CPU_HEADS", heads))
+        Q, K, V = (rng.uniform(-1, 1, (heads, L, d)).astype(np.float32) for _ in range(3))
+        t0 = time.perf_counter()
+        for h in range(heads):
+            reference.naive_attention(Q[h], K[h], V[h])
+        secs = time.perf_counter() - t0
+        res["naive_attention_numpy"] = {"heads": heads, "seconds": round(secs, 3), "dtype": "f32",
+                                        "tflops": round(flops(1, heads, L, d) / secs / 1e12, 5),
+                                        "extrapolated_full_batch_seconds": round(secs * n_heads / heads, 1)}
+        if (L // 8) ** 2 <= 32768:
+            O = np.zeros(L * d, dtype=np.float32)
+            t0 = time.perf_counter()
+            tiled.flash_attention_tiled(Q[0].reshape(-1), K[0].reshape(-1), V[0].reshape(-1), O, L, d, 8, 8)
+            secs = time.perf_counter() - t0
+            res["numpy_gpu_like_opt2_port_Bq8_Bk8"] = {"heads": 1, "seconds": round(secs, 3), "dtype": "f32", "threads": 1,
+                                                       "tflops": round(flops(1, 1, L, d) / secs / 1e12, 6),
+                                                       "extrapolated_full_batch_seconds": round(secs * n_heads, 1)}
+    except Exception as e:  # noqa: BLE001
+        res["error"] = str(e)[:200]
+    return res
 
 
 def run_reference(args):

@@ -16,9 +16,6 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_combine_sm100.cuh"
-#include "fa_fwd_pair2_sm100.cuh"
-#include "fa_fwd_pair4_sm100.cuh"
-#include "fa_fwd_pair_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_tiled_d_pair_sm100.cuh"
 #include "fa_tiled_d_sm100.cuh"
@@ -28,8 +25,10 @@
                                     // B16 H8 L4096); d = 256 stays on the slab kernel (1340 vs 680)
 #endif
 
-#ifndef FA_FWD_PAIR_DEFAULT
-#define FA_FWD_PAIR_DEFAULT 0       // 1: dense 16-bit d = 128 forward runs on CTA pairs (fa_fwd_pair_sm100.cuh)
+#ifdef FA_TRACE
+// Tuning builds only (never the shipped library): device buffer the fused-tile kernel's CTA 0 writes SM-clock stamps to.
+static long long* g_trace = nullptr;
+extern "C" void fa_debug_set_trace(void* dev_buf) { g_trace = static_cast<long long*>(dev_buf); }
 #endif
 
 namespace {
@@ -125,100 +124,10 @@ struct FwdExtra {
   long long q_head_rows = 0, kv_head_rows = 0, out_head_rows = 0;
 };
 
-// K1P: dense d = 128 forward on CTA pairs (both SMs of a pair share every K / V tile through 2-CTA MMAs).
-// FA_B200_FWD_PAIR = 0 / 1 / 2 / 3 overrides the compiled default (read once per process); 2 = the experimental K1Q,
-// 3 = K1R (K1Q with four softmax warpgroups; UNVERIFIED on a GPU, see fa_fwd_pair4_sm100.cuh).
-int fwd_pair_mode() {
-  static const int mode = [] {
-    const char* e = std::getenv("FA_B200_FWD_PAIR");
-    return e ? std::atoi(e) : FA_FWD_PAIR_DEFAULT;
-  }();
-  return mode;
-}
-
-template <int DT>
-int launch_fwd_pair(const void* Q, const void* K, const void* V, void* O, int BH, int L, float* lse_out,
-                    cudaStream_t stream) {
-  using T = fa::FwdPairTraits<DT>;
-  constexpr int D = 128;
-  CUtensorMap tmQ, tmK, tmV, tmO;
-  int rc;
-  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmK, K, DT, D, L, BH, 64)) != FA_OK) return rc;    // each CTA: its 64 keys of a tile
-  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
-  if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) return rc;
-  fa::FwdParams p{};
-  p.L = L;
-  p.Lk = L;
-  p.BH = BH;
-  p.H = 1;
-  p.kv_per_split = L;
-  p.n_splits = 1;
-  p.n_qpairs = (L + 255) / 256;
-  const long long items = (long long)BH * ((p.n_qpairs + 1) / 2);
-  if (items > 0x3fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-block) work items");
-  p.n_items = int(items);
-  p.scale = 1.0f / std::sqrt(float(D));
-  p.scale_log2 = p.scale * 1.4426950408889634f;
-  p.lse_out = lse_out;
-  p.out_head_rows = L;
-  auto kern = fa::fa_fwd_pair_kernel<DT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-  const int sms = sm_count();
-  if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
-  const int pairs = p.n_items < sms / 2 ? p.n_items : sms / 2;   // persistent: one CTA pair per SM pair
-  kern<<<2 * pairs, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);   // __cluster_dims__(2, 1, 1)
-  FA_CUDA_TRY(cudaGetLastError());
-  return FA_OK;
-}
-
-// K1Q (experimental, FA_B200_FWD_PAIR=2): one Q tile per CTA of a pair, S and P double-buffered (fa_fwd_pair2_sm100.cuh).
-template <int DT, bool FOUR_WG>
-int launch_fwd_pair2(const void* Q, const void* K, const void* V, void* O, int BH, int L, float* lse_out,
-                     cudaStream_t stream) {
-  using T = std::conditional_t<FOUR_WG, fa::FwdPair4Traits<DT>, fa::FwdPair2Traits<DT>>;
-  constexpr int D = 128;
-  CUtensorMap tmQ, tmK, tmV, tmO;
-  int rc;
-  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmK, K, DT, D, L, BH, 64)) != FA_OK) return rc;
-  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
-  if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) return rc;
-  fa::FwdParams p{};
-  p.L = L;
-  p.Lk = L;
-  p.BH = BH;
-  p.H = 1;
-  p.kv_per_split = L;
-  p.n_splits = 1;
-  const long long items = (long long)BH * ((L + 255) / 256);
-  if (items > 0x3fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-block) work items");
-  p.n_items = int(items);
-  p.scale = 1.0f / std::sqrt(float(D));
-  p.scale_log2 = p.scale * 1.4426950408889634f;
-  p.lse_out = lse_out;
-  p.out_head_rows = L;
-  auto kern = FOUR_WG ? fa::fa_fwd_pair4_kernel<DT> : fa::fa_fwd_pair2_kernel<DT>;   // K1R (unverified) / K1Q
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-  const int sms = sm_count();
-  if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
-  const int pairs = p.n_items < sms / 2 ? p.n_items : sms / 2;
-  kern<<<2 * pairs, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);   // __cluster_dims__(2, 1, 1)
-  FA_CUDA_TRY(cudaGetLastError());
-  return FA_OK;
-}
-
 template <int D, int DT, bool SPLIT>
 int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int L, int kv_per_split, int n_splits,
                float* o_accum, float* lse_accum, cudaStream_t stream, float* lse_out = nullptr, int causal = 0,
                const FwdExtra& ex = FwdExtra()) {
-  if constexpr (!SPLIT && D == 128 && DT != fa::DT_F32) {
-    if (fwd_pair_mode() >= 1 && !causal && ex.kv_lens == nullptr && (ex.Lk == 0 || ex.Lk == L) && ex.q_head_rows == 0 &&
-        ex.kv_head_rows == 0 && ex.out_head_rows == 0)
-      return fwd_pair_mode() == 3   ? launch_fwd_pair2<DT, true>(Q, K, V, O, BH, L, lse_out, stream)
-             : fwd_pair_mode() == 2 ? launch_fwd_pair2<DT, false>(Q, K, V, O, BH, L, lse_out, stream)
-                                    : launch_fwd_pair<DT>(Q, K, V, O, BH, L, lse_out, stream);
-  }
   using T = fa::FwdTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
@@ -250,6 +159,9 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.lse_out = SPLIT ? nullptr : lse_out;
   p.causal = (SPLIT && (n_splits != 1 || Lk != L)) ? 0 : causal;
   p.out_head_rows = int(ex.out_head_rows > 0 ? ex.out_head_rows : L);
+#ifdef FA_TRACE
+  p.trace = g_trace;
+#endif
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...

@@ -55,7 +55,24 @@ struct FwdParams {
   int causal;        // != 0: query row r attends to keys 0..r only   (SPLIT: only with n_splits == 1 and L == Lk)
   int out_head_rows; // SPLIT: rows between consecutive heads of o_accum / lse_accum (== L unless the caller writes into a
                      // row window of a taller partial buffer)
+  long long* trace;  // FA_TRACE builds only: [3 roles][256 tiles][8 slots] SM-clock stamps of CTA 0 (tests/gpu_probe/trace_k1.py)
 };
+
+#ifdef FA_TRACE
+// SM cycle counter read that cannot be hoisted above the computation of `dep`.
+__device__ __forceinline__ long long trace_clock(uint32_t dep = 0) {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
+#define FA_TR(role, tile, slot, dep)                                                              \
+  do {                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 256)                                    \
+      p.trace[((role) * 256 + (tile)) * 8 + (slot)] = trace_clock(dep);                           \
+  } while (0)
+#else
+#define FA_TR(role, tile, slot, dep) do { } while (0)
+#endif
 
 // (Tried and dropped: O rows straight from registers to global to buy a 5th K/V ring stage — the row-strided 16-byte
 //  stores cost 11 % at L=1024 for +1 % at L=16384.)
@@ -382,10 +399,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 mbar_wait(&o_free[i], (ni[i] - 1) & 1);
               }
               mbar_wait(&p_full[2 * i], nt[i] & 1);
+              FA_TR(2, nt[i], 4 * i + 0, 0);
               tc_fence_after();
               if (FA_P_HALVES) {
                 pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+                FA_TR(2, nt[i], 4 * i + 1, 0);
                 mbar_wait(&p_full[2 * i + 1], nt[i] & 1);
+                FA_TR(2, nt[i], 4 * i + 2, 0);
                 tc_fence_after();
                 pv(i, tv % NS, 1u, KT / 2, KT);
               } else {
@@ -400,6 +420,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
                 qk(i, tk % NS);
                 tc_commit(&s_full[i]);
+                FA_TR(2, nt[i] - 1, 4 * i + 3, 0);
                 if (j + 2 == c.nt[i]) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
               } else {
                 tc_commit(&o_done[i]);
@@ -439,11 +460,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int row_q = c.q_row0 + i * BM + row;   // my query row inside the head
       for (int j = 0; j < my_tiles; ++j, ++nt) {
         mbar_wait(&s_full[i], nt & 1);
+        if (row == 0) FA_TR(i, nt, 0, 0);
         tc_fence_after();
         uint32_t s[4][32];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s[cc]);
         tc_wait_ld();
+        if (row == 0) FA_TR(i, nt, 1, s[3][31]);
         if constexpr (T::SEP_P) {
           tc_fence_before();
           mbar_arrive(&s_free[i]);  // S_i(j) is in registers: QK_i(j+1) may overwrite it while this tile's exp runs
@@ -480,6 +503,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           asm volatile("" ::: "memory");  // keep this a real branch
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (row == 0) FA_TR(i, nt, 2, __float_as_uint(mx));
         if constexpr (T::SEP_P) {
           // QK_i(j) was issued ahead of PV_i(j-1) here, so s_full no longer implies that PV retired: wait for it before
           // O_i is rescaled or P_i overwritten (it was issued a whole tile period ago; this does not spin in steady state).
@@ -567,15 +591,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         };
         if (FA_P_HALVES) {
           exp_blocks(0, 2);
+          if (row == 0) FA_TR(i, nt, 3, s[1][31]);
           store_p(0, 2);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&p_full[2 * i]);
+          if (row == 0) FA_TR(i, nt, 4, 0);
           exp_blocks(2, 4);
+          if (row == 0) FA_TR(i, nt, 5, s[3][31]);
           store_p(2, 4);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&p_full[2 * i + 1]);
+          if (row == 0) FA_TR(i, nt, 6, 0);
         } else {
           exp_blocks(0, 4);
           store_p(0, 4);

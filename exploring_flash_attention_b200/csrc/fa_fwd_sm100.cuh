@@ -113,12 +113,20 @@ struct FwdTraits {
 #ifndef FA_P_HALVES
 #define FA_P_HALVES 1   // 1: publish P in two 64-key halves so the first half of PV overlaps the second half of exp
 #endif
+#ifndef FA_P_SPLIT
+#define FA_P_SPLIT 2    // 32-key blocks of P in the first published part (2: halves; 3: three quarters then one quarter,
+                        // measured +-0 on B200)
+#endif
 #ifndef FA_PACKED
 #define FA_PACKED 1     // 1: packed fp32x2 FFMA2 / FADD2 for the scale-subtract and the row sum (halves their issue slots)
 #endif
 
-// (Tried and dropped: issuing the next item's first QK^T right behind this item's last PV — +3 % for 1-tile items,
-//  -2 % at d=128 / L>=1024.)
+// (Tried and dropped, round 2 re-measured without register spills: issuing the next item's first QK_i right behind this
+//  item's last PV_i — C4 slice +1 %, C2 +-0, causal C2 -3.5 %.  One tcgen05.mma issuing warp per Q tile: the tiles fall into
+//  lock-step (both exponentiate, then both queue MMAs), period 3200 -> 3860 cycles; pacing the softmax warpgroups against
+//  each other restores the offset but not the period (3550).  Speculative exponentials against the running max with the
+//  row-max FMNMX stream folded beside them (redo from TMEM when a row's max really moves): -8 %, the two code paths cost
+//  registers and the compiler does not interleave the streams.  The per-Q-tile chain QK -> softmax -> PV bounds K1.)
 
 #ifndef FA_POLY_MOD
 #define FA_POLY_MOD 4   // N > 0: one element pair in N takes exp2 on the FMA pipes (Cody-Waite + degree-3 polynomial);
@@ -147,7 +155,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 
 struct ItemCoord {
   int q_row0, bh, split, kv_begin, kv_end, n_tiles, n_q;
-  int nt[2];  // KV tiles Q tile i actually needs (causal: up to its diagonal tile); n_tiles = the larger of the two
+  int nt0, nt1;  // KV tiles Q tile 0 / 1 actually needs (causal: up to its diagonal tile); n_tiles = the larger of the two
+  // (not an array: a runtime index put the struct in local memory and left LDL/STL in every role's loop)
+  __device__ __forceinline__ int nt(int i) const { return i ? nt1 : nt0; }
 };
 
 template <bool SPLIT>
@@ -171,11 +181,11 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const FwdParams& p) {
   c.kv_end = SPLIT ? min(kv_len, c.kv_begin + p.kv_per_split) : kv_len;
   c.n_tiles = (c.kv_end - c.kv_begin + 127) / 128;
   c.n_q = (p.L - c.q_row0 > 128) ? 2 : 1;
-  c.nt[0] = c.nt[1] = c.n_tiles;
+  c.nt0 = c.nt1 = c.n_tiles;
   if (p.causal) {
-    c.nt[0] = min(c.n_tiles, c.q_row0 / 128 + 1);
-    c.nt[1] = min(c.n_tiles, c.q_row0 / 128 + 2);
-    c.n_tiles = c.n_q > 1 ? c.nt[1] : c.nt[0];
+    c.nt0 = min(c.n_tiles, c.q_row0 / 128 + 1);
+    c.nt1 = min(c.n_tiles, c.q_row0 / 128 + 2);
+    c.n_tiles = c.n_q > 1 ? c.nt1 : c.nt0;
   }
   return c;
 }
@@ -287,11 +297,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // exist in the 128B-swizzle / 32B-atom layout (4-key atoms, 512 B apart) — V's tensor map matches (fa_api.cu).
         constexpr uint64_t hiV = (DT == DT_F32) ? make_smem_desc_hi(BLK_BYTES, 512, SWZ_128B_BASE32B)
                                                 : make_smem_desc_hi(BLK_BYTES, 8 * T::SWB, T::SWZ);
-        constexpr int KT = BN / UK;
-        const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+        constexpr int KT = BN / UK;                 // MMA K-steps per KV tile
+        constexpr int KS = FA_P_SPLIT * 32 / UK;     // ... of which the first published part of P covers KS
+        const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV), tmem_base_ = tmem_base;
 
+        // With P aliased over S the issuer sits on the per-tile critical chain.  Left to itself the compiler hoists every
+        // per-K-step descriptor / TMEM address out of the item loop, runs out of this warpgroup's 72 registers and
+        // reloads them from local memory (LDL) between "P is ready" and the first MMA; recomputing them from `opaque`
+        // bases is a few integer adds (C2 +1 %, C3 +5 %, causal +3 %).  The SEP_P schedule was faster with the hoisting.
+        auto opaque = [](uint32_t v) {
+          if constexpr (!T::SEP_P) asm volatile("" : "+r"(v));
+          return v;
+        };
         auto qk = [&](int i, int stage) {  // S_i = Q_i K^T
-          const uint32_t a_base = sQ_addr + i * TILE_BYTES, b_base = sKV_addr + stage * TILE_BYTES;
+          const uint32_t a_base = opaque(sQ_addr) + i * TILE_BYTES, b_base = opaque(sKV_addr) + stage * TILE_BYTES;
+          const uint32_t tmem_base = opaque(tmem_base_);
 #pragma unroll
           for (int k = 0; k < D / UK; ++k) {
             const uint32_t off = (k / T::KPR) * BLK_BYTES + (k % T::KPR) * 32;
@@ -300,7 +320,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         };
         auto pv = [&](int i, int stage, uint32_t acc, int kk0, int kk1) {  // O_i (+)= P_i V  (K-steps kk0..kk1-1)
-          const uint32_t b_base = sKV_addr + stage * TILE_BYTES;
+          const uint32_t b_base = opaque(sKV_addr) + stage * TILE_BYTES;
+          const uint32_t tmem_base = opaque(tmem_base_);
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
             umma_ts<KIND>(tmem_base + T::TM_O + i * D, tmem_base + T::TM_P + i * T::P_STRIDE + kk * (UK * T::ES / 4),
@@ -328,7 +349,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               qk(i, t0 % NS);
               tc_commit(&s_full[i]);
               ++nqk[i];
-              if (c.nt[i] == 1) tc_commit(&q_empty[i]);
+              if (c.nt(i) == 1) tc_commit(&q_empty[i]);
             }
             tc_commit(&kv_empty[t0 % NS]);
             for (int j = 0; j < c.n_tiles; ++j) {
@@ -337,34 +358,34 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                  if (i >= c.n_q || j + 1 >= c.nt[i]) continue;
+                  if (i >= c.n_q || j + 1 >= c.nt(i)) continue;
                   mbar_wait(&s_free[i], (nqk[i] - 1) & 1);
                   tc_fence_after();
                   qk(i, tk % NS);
                   tc_commit(&s_full[i]);
                   ++nqk[i];
-                  if (j + 2 == c.nt[i]) tc_commit(&q_empty[i]);
+                  if (j + 2 == c.nt(i)) tc_commit(&q_empty[i]);
                 }
                 tc_commit(&kv_empty[tk % NS]);
               }
               mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                if (i >= c.n_q || j >= c.nt[i]) continue;
+                if (i >= c.n_q || j >= c.nt(i)) continue;
                 if (j == 0 && ni[i] > 0) mbar_wait(&o_free[i], (ni[i] - 1) & 1);
                 mbar_wait(&p_full[2 * i], nt[i] & 1);
                 tc_fence_after();
                 if (FA_P_HALVES) {
-                  pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+                  pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KS);
                   mbar_wait(&p_full[2 * i + 1], nt[i] & 1);
                   tc_fence_after();
-                  pv(i, tv % NS, 1u, KT / 2, KT);
+                  pv(i, tv % NS, 1u, KS, KT);
                 } else {
                   pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
                 }
                 ++nt[i];
                 tc_commit(&pv_done[i]);
-                if (j + 1 == c.nt[i]) tc_commit(&o_done[i]);
+                if (j + 1 == c.nt(i)) tc_commit(&o_done[i]);
               }
               tc_commit(&kv_empty[tv % NS]);
             }
@@ -384,7 +405,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             tc_fence_after();
             qk(i, t0 % NS);
             tc_commit(&s_full[i]);
-            if (c.nt[i] == 1) tc_commit(&q_empty[i]);
+            if (c.nt(i) == 1) tc_commit(&q_empty[i]);
           }
           tc_commit(&kv_empty[t0 % NS]);  // K_0: both QK(0) are issued by now
           for (int j = 0; j < c.n_tiles; ++j) {
@@ -393,7 +414,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_wait(&kv_full[tv % NS], (tv / NS) & 1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              if (i >= c.n_q || j >= c.nt[i]) continue;  // causal: tile 0 stops one KV tile before tile 1
+              if (i >= c.n_q || j >= c.nt(i)) continue;  // causal: tile 0 stops one KV tile before tile 1
               if (j == 0 && ni[i] > 0) {
                 // PV_i(0) overwrites O_i: the previous item's epilogue must have read it out of TMEM
                 mbar_wait(&o_free[i], (ni[i] - 1) & 1);
@@ -402,17 +423,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               FA_TR(2, nt[i], 4 * i + 0, 0);
               tc_fence_after();
               if (FA_P_HALVES) {
-                pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT / 2);
+                pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KS);
                 FA_TR(2, nt[i], 4 * i + 1, 0);
                 mbar_wait(&p_full[2 * i + 1], nt[i] & 1);
                 FA_TR(2, nt[i], 4 * i + 2, 0);
                 tc_fence_after();
-                pv(i, tv % NS, 1u, KT / 2, KT);
+                pv(i, tv % NS, 1u, KS, KT);
               } else {
                 pv(i, tv % NS, j > 0 ? 1u : 0u, 0, KT);
               }
               ++nt[i];
-              if (j + 1 < c.nt[i]) {
+              if (j + 1 < c.nt(i)) {
                 if (!k_waited) {
                   mbar_wait(&kv_full[tk % NS], (tk / NS) & 1);
                   tc_fence_after();
@@ -421,7 +442,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 qk(i, tk % NS);
                 tc_commit(&s_full[i]);
                 FA_TR(2, nt[i] - 1, 4 * i + 3, 0);
-                if (j + 2 == c.nt[i]) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
+                if (j + 2 == c.nt(i)) tc_commit(&q_empty[i]);  // that was the last QK_i of this item
               } else {
                 tc_commit(&o_done[i]);
               }
@@ -456,7 +477,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       float m_used = -CUDART_INF_F;
       float l = 0.f;
 
-      const int my_tiles = c.nt[i];
+      const int my_tiles = c.nt(i);
       const int row_q = c.q_row0 + i * BM + row;   // my query row inside the head
       for (int j = 0; j < my_tiles; ++j, ++nt) {
         mbar_wait(&s_full[i], nt & 1);
@@ -472,14 +493,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           mbar_arrive(&s_free[i]);  // S_i(j) is in registers: QK_i(j+1) may overwrite it while this tile's exp runs
         }
 
-        // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
-        // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
         // valid = number of leading columns of this tile my row may attend to: the ragged end of the key range and,
         // when causal, the diagonal (key index <= query row); only the last tile of a row can be cut.
         int valid = c.kv_end - (c.kv_begin + j * BN);
         if (p.causal) valid = min(valid, row_q - j * BN + 1);
-        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
-        if (__all_sync(0xffffffffu, valid >= BN)) {
+        const bool full_tile = __all_sync(0xffffffffu, valid >= BN);
+        auto row_max = [&]() {   // four independent FMNMX3 streams
+          float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
             mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
@@ -487,59 +507,28 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
             mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
           }
-        } else {
+          return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        };
+        // Moves the running max to mx on the rows that `need` it and rescales l and O_i (in TMEM) on those rows.
+        // PV_i(j-1) has retired, so O_i is quiescent: without SEP_P s_full[i](j) implies it (same issuing thread, in-order
+        // pipe); with SEP_P the pv_done wait below does.
+        auto rescale = [&](float mx, bool need) {
+          const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
+          if (need) m_used = mx;
+          l *= alpha;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
+          for (int cc = 0; cc < D / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tc_wait_ld();
 #pragma unroll
-            for (int x = 0; x < 32; ++x)
-              if (cc * 32 + x >= valid) s[cc][x] = __float_as_uint(-CUDART_INF_F);
-#pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            mx0 = fmaxf(mx0, __uint_as_float(s[0][x]));
-            mx1 = fmaxf(mx1, __uint_as_float(s[1][x]));
-            mx2 = fmaxf(mx2, __uint_as_float(s[2][x]));
-            mx3 = fmaxf(mx3, __uint_as_float(s[3][x]));
+            for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+            tmem_st32(tO + cc * 32, o);
           }
-          asm volatile("" ::: "memory");  // keep this a real branch
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (row == 0) FA_TR(i, nt, 2, __float_as_uint(mx));
-        if constexpr (T::SEP_P) {
-          // QK_i(j) was issued ahead of PV_i(j-1) here, so s_full no longer implies that PV retired: wait for it before
-          // O_i is rescaled or P_i overwritten (it was issued a whole tile period ago; this does not spin in steady state).
-          if (nt > 0) {
-            mbar_wait(&pv_done[i], (nt - 1) & 1);
-            tc_fence_after();
-          }
-        }
-
-        if (j == 0) {
-          m_used = mx;
-        } else {
-          // Lazy rescale: keep the stale max unless the new one is > 2^8 larger (in exp2 units).
-          const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            // PV_i(j-1) has retired, so O_i is quiescent: without SEP_P s_full[i](j) implies it (same issuing thread,
-            // in-order pipe); with SEP_P the pv_done wait above does.
-            const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
-            if (need) m_used = mx;
-            l *= alpha;
-#pragma unroll
-            for (int cc = 0; cc < D / 32; ++cc) {
-              uint32_t o[32];
-              tmem_ld32(tO + cc * 32, o);
-              tc_wait_ld();
-#pragma unroll
-              for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-              tmem_st32(tO + cc * 32, o);
-            }
-          }
-        }
-
-        const float neg_m = -m_used * p.scale_log2;
+        };
         // p = 2^(s*scale_log2 - m*scale_log2): column blocks c0..c1-1 of s, four independent streams per step
         float2 lsum[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-        auto exp_blocks = [&](int c0, int c1) {
+        auto exp_blocks = [&](int c0, int c1, float neg_m) {
 #pragma unroll
           for (int x = 0; x < 32; x += 2) {
 #pragma unroll
@@ -570,46 +559,85 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
           }
         };
-        auto store_p = [&](int c0, int c1) {  // P columns 32*c0 .. 32*c1-1 -> TMEM (in place over S)
+        auto pack_block = [&](int cc, uint32_t* pk) {   // 32 fp32 P values of block cc -> 16 packed 16-bit pairs
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const float a = __uint_as_float(s[cc][2 * x]), b = __uint_as_float(s[cc][2 * x + 1]);
+            pk[x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+          }
+        };
+        auto store_p = [&](int c0, int c1) {  // P key blocks c0 .. c1-1 -> TMEM (in place over S unless SEP_P)
           if constexpr (DT == DT_F32) {
 #pragma unroll
             for (int cc = c0; cc < c1; ++cc) tmem_st32(tS + cc * 32, s[cc]);
-          } else {
+          } else {   // 16 packed columns per key block
 #pragma unroll
-            for (int cc = c0; cc < c1; cc += 2) {
-              uint32_t pk[32];
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int x = 0; x < 16; ++x) {
-                  const float a = __uint_as_float(s[cc + h][2 * x]), b = __uint_as_float(s[cc + h][2 * x + 1]);
-                  pk[h * 16 + x] = (DT == DT_BF16) ? pack_bf16x2(a, b) : pack_f16x2(a, b);
-                }
-              tmem_st32(tP + (cc / 2) * 32, pk);
+            for (int cc = c0; cc < c1; ++cc) {
+              if ((cc & 1) == 0 && cc + 1 < c1) {
+                uint32_t pk[32];
+                pack_block(cc, pk);
+                pack_block(cc + 1, pk + 16);
+                tmem_st32(tP + cc * 16, pk);
+              } else if ((cc & 1) == 1 && cc > c0) {
+                // second block of a pair stored above
+              } else {
+                uint32_t pk[16];
+                pack_block(cc, pk);
+                tmem_st16(tP + cc * 16, pk);
+              }
             }
           }
         };
-        if (FA_P_HALVES) {
-          exp_blocks(0, 2);
-          if (row == 0) FA_TR(i, nt, 3, s[1][31]);
-          store_p(0, 2);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&p_full[2 * i]);
-          if (row == 0) FA_TR(i, nt, 4, 0);
-          exp_blocks(2, 4);
+        constexpr int P1 = FA_P_HALVES ? FA_P_SPLIT : 4;   // key blocks in the first published part of P
+
+        {
+          // Row max.  Only the last tile of a key range can be ragged; its masking (128 compare+select pairs) lives in
+          // its own branch together with a copy of the max tree so the compiler cannot if-convert it into every tile.
+          float mx;
+          if (full_tile) {
+            mx = row_max();
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+              for (int x = 0; x < 32; ++x)
+                if (cc * 32 + x >= valid) s[cc][x] = __float_as_uint(-CUDART_INF_F);
+            mx = row_max();
+            asm volatile("" ::: "memory");  // keep this a real branch
+          }
+          if (row == 0) FA_TR(i, nt, 2, __float_as_uint(mx));
+          if constexpr (T::SEP_P) {
+            // QK_i(j) was issued ahead of PV_i(j-1) here, so s_full no longer implies that PV retired: wait for it before
+            // O_i is rescaled or P_i overwritten (it was issued a whole tile period ago; this does not spin in steady state).
+            if (nt > 0) {
+              mbar_wait(&pv_done[i], (nt - 1) & 1);
+              tc_fence_after();
+            }
+          }
+          if (j == 0) {
+            m_used = mx;
+          } else {
+            // Lazy rescale: keep the stale max unless the new one is > 2^8 larger (in exp2 units).
+            const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
+            if (__any_sync(0xffffffffu, need)) rescale(mx, need);
+          }
+          exp_blocks(0, P1, -m_used * p.scale_log2);
+        }
+        const float neg_m = -m_used * p.scale_log2;
+        if (row == 0) FA_TR(i, nt, 3, s[P1 - 1][31]);
+        store_p(0, P1);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[2 * i]);
+        if (row == 0) FA_TR(i, nt, 4, 0);
+        if (P1 < 4) {
+          exp_blocks(P1, 4, neg_m);
           if (row == 0) FA_TR(i, nt, 5, s[3][31]);
-          store_p(2, 4);
+          store_p(P1, 4);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&p_full[2 * i + 1]);
           if (row == 0) FA_TR(i, nt, 6, 0);
-        } else {
-          exp_blocks(0, 4);
-          store_p(0, 4);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&p_full[2 * i]);
         }
         l += ((lsum[0].x + lsum[0].y) + (lsum[1].x + lsum[1].y)) + ((lsum[2].x + lsum[2].y) + (lsum[3].x + lsum[3].y));
       }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -66,23 +67,47 @@ EncodeFn get_encode_fn() {
 int elem_size(int dtype) { return dtype == FA_DTYPE_F32 ? 4 : 2; }
 
 // SM count of the current device, queried once per device (not per call like the reference's
-// cudaGetDeviceProperties, flash_attention_v1.h:280-281).
-int sm_count() {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-  if (cached[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    cached[dev] = n;
-  }
-  return cached[dev];
+// cudaGetDeviceProperties, flash_attention_v1.h:280-281).  The per-device slots are atomics: two host threads racing on
+// the first call both store the same value.
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
 }
+
+int sm_count() {
+  static std::atomic<int> cached[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of on every launch:
+// each launch_* template instantiation owns one of these.
+struct SmemAttrOnce {
+  std::atomic<unsigned long long> done{0};
+  template <typename Kern>
+  int ensure(Kern kern, int bytes) {
+    const int dev = current_device();
+    if (dev < 0) return fail(FA_ERR_CUDA, "cannot query the current device");
+    if ((done.load(std::memory_order_acquire) >> dev) & 1ull) return FA_OK;
+    FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(1ull << dev, std::memory_order_release);
+    return FA_OK;
+  }
+};
 
 // [BH][L][D] row-major tensor, box = one 128-byte-wide, `box_rows`-row block of one head, 128B swizzle.
 // Rows past L are zero-filled on load and clipped on store, so tiles never leak into the next head.
-int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false,
-             long long head_stride_rows = 0 /* rows between consecutive heads; 0 = L (dense) */) {
+int encode_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand,
+               long long head_stride_rows) {
   EncodeFn enc = get_encode_fn();
   if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = elem_size(dtype);
@@ -101,6 +126,47 @@ int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, i
   CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return FA_OK;
+}
+
+// A tensor map is a pure function of (pointer, dtype, shape, box, layout): callers that launch on the same buffers step
+// after step (every training / serving loop) get it from a small per-thread direct-mapped cache instead of a driver call
+// per operand per launch (the reference re-derives all launch state per call, flash_attention_v1.h:280-292).
+struct MapKey {
+  const void* ptr;
+  long long head_stride_rows;
+  int dtype, D, L, BH, box_rows, mn_major;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && head_stride_rows == o.head_stride_rows && dtype == o.dtype && D == o.D && L == o.L &&
+           BH == o.BH && box_rows == o.box_rows && mn_major == o.mn_major;
+  }
+};
+struct MapSlot {
+  MapKey key{};
+  bool valid = false;
+  alignas(64) CUtensorMap map;
+};
+constexpr int kMapCacheSlots = 64;
+std::atomic<unsigned long long> g_map_hits{0}, g_map_misses{0};
+
+int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false,
+             long long head_stride_rows = 0 /* rows between consecutive heads; 0 = L (dense) */) {
+  thread_local MapSlot cache[kMapCacheSlots];
+  const MapKey key{ptr, head_stride_rows, dtype, D, L, BH, box_rows, mn_major_operand ? 1 : 0};
+  unsigned long long h = reinterpret_cast<uintptr_t>(ptr) >> 8;
+  h = (h ^ (h >> 17)) * 0x9E3779B97F4A7C15ull + (unsigned long long)(box_rows * 31 + (mn_major_operand ? 7 : 0) + L * 131 + BH);
+  MapSlot& slot = cache[(h >> 20) % kMapCacheSlots];
+  if (slot.valid && slot.key == key) {
+    *m = slot.map;
+    g_map_hits.fetch_add(1, std::memory_order_relaxed);
+    return FA_OK;
+  }
+  const int rc = encode_map(m, ptr, dtype, D, L, BH, box_rows, mn_major_operand, head_stride_rows);
+  if (rc != FA_OK) return rc;
+  slot.key = key;
+  slot.map = *m;
+  slot.valid = true;
+  g_map_misses.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
 }
 
@@ -163,7 +229,8 @@ int launch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, int
   p.trace = g_trace;
 #endif
   auto kern = fa::fa_fwd_kernel<D, DT, SPLIT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  static SmemAttrOnce smem_attr;
+  if ((rc = smem_attr.ensure(kern, T::SMEM_BYTES)) != FA_OK) return rc;
   // persistent: one CTA per SM (smem and TMEM admit exactly one), each walking items blockIdx.x, +gridDim.x, ...
   const int sms = sm_count();
   if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
@@ -195,32 +262,54 @@ int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, i
                   std::to_string(d) + " dtype=" + std::to_string(dtype));
 }
 
+// Optional arguments of the slab tiled-d kernel beyond the reference's dense (Q,K,V,O): key ranges (V2 splits / partials),
+// causal masking, the log-sum-exp output.
+struct TiledDExtra {
+  int kv_per_split = 0, n_splits = 1;   // kv_per_split 0: one range covering every key
+  float* o_accum = nullptr;             // non-null: fp32 partial rows + lse_accum instead of O
+  float* lse_accum = nullptr;
+  float* lse_out = nullptr;
+  int causal = 0;
+  FwdExtra fx;
+};
+
 template <int D, int DT>
-int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream) {
+int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream,
+                   const TiledDExtra& ex = TiledDExtra()) {
   using T = fa::TiledDTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
-  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
-  if ((rc = make_map(&tmV, V, DT, D, L, BH, 128, /*mn_major_operand=*/true)) != FA_OK) return rc;
-  if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) return rc;
+  const int Lk = ex.fx.Lk > 0 ? ex.fx.Lk : L;
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128, false, ex.fx.q_head_rows)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, Lk, BH, 128, false, ex.fx.kv_head_rows)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, Lk, BH, 128, /*mn_major_operand=*/true, ex.fx.kv_head_rows)) != FA_OK) return rc;
+  if (ex.o_accum != nullptr) {
+    tmO = tmQ;  // unused by the partial epilogue
+  } else if ((rc = make_map(&tmO, O, DT, D, L, BH, 128)) != FA_OK) {
+    return rc;
+  }
   fa::FwdParams p{};
   p.L = L;
+  p.Lk = Lk;
   p.BH = BH;
-  p.kv_per_split = L;
-  p.n_splits = 1;
+  p.H = ex.fx.H > 0 ? ex.fx.H : 1;
+  p.kv_lens = ex.o_accum ? nullptr : ex.fx.kv_lens;
+  p.kv_per_split = ex.kv_per_split > 0 ? ex.kv_per_split : Lk;
+  p.n_splits = ex.n_splits;
   p.n_qpairs = 0;
   p.n_items = 0;
   p.scale = 1.0f / std::sqrt(float(D));
   p.scale_log2 = p.scale * 1.4426950408889634f;
-  p.o_accum = nullptr;
-  p.lse_accum = nullptr;
-  p.lse_out = nullptr;
-  p.causal = 0;
+  p.o_accum = ex.o_accum;
+  p.lse_accum = ex.lse_accum;
+  p.lse_out = ex.o_accum ? nullptr : ex.lse_out;
+  p.causal = (ex.n_splits == 1 && Lk == L) ? ex.causal : 0;
+  p.out_head_rows = int(ex.fx.out_head_rows > 0 ? ex.fx.out_head_rows : L);
   auto kern = fa::fa_tiled_d_kernel<D, DT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-  const long long blocks = (long long)((L + 127) / 128) * BH * T::NSLAB;
-  if (blocks > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-tile, slab) blocks");
+  static SmemAttrOnce smem_attr;
+  if ((rc = smem_attr.ensure(kern, T::SMEM_BYTES)) != FA_OK) return rc;
+  const long long blocks = (long long)((L + 127) / 128) * BH * ex.n_splits * T::NSLAB;
+  if (blocks > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, split, q-tile, slab) blocks");
   dim3 grid((unsigned)blocks);
   kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   FA_CUDA_TRY(cudaGetLastError());
@@ -246,7 +335,8 @@ int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, in
   p.scale = 1.0f / std::sqrt(float(D));
   p.scale_log2 = p.scale * 1.4426950408889634f;
   auto kern = fa::fa_tiled_d_pair_kernel<D, DT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  static SmemAttrOnce smem_attr;
+  if ((rc = smem_attr.ensure(kern, T::SMEM_BYTES)) != FA_OK) return rc;
   const long long blocks = 2LL * ((L + 127) / 128) * BH;   // the kernel carries __cluster_dims__(2, 1, 1)
   if (blocks > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, q-tile) CTA pairs");
   kern<<<dim3((unsigned)blocks), T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
@@ -254,16 +344,33 @@ int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, in
   return FA_OK;
 }
 
-// Which kernel serves 16-bit d = 512 / 256: FA_B200_TILED_D_PAIR=1 selects the CTA-pair kernel for d = 512,
-// =2 for d = 256 as well, =0 the single-CTA slab kernel.  Read once per process.
+// Which kernel serves 16-bit d = 512 / 256: FA_B200_TILED_D_PAIR=1 (the default) selects the CTA-pair kernel for d = 512,
+// =2 for d = 256 as well, =0 the single-CTA slab kernel.  Read once per process; any other value is ignored.
 int tiled_d_pair_mode() {
   static const int mode = [] {
     const char* e = std::getenv("FA_B200_TILED_D_PAIR");
-    return e ? std::atoi(e) : FA_TILED_D_PAIR_DEFAULT;
+    if (e == nullptr || e[0] == '\0') return FA_TILED_D_PAIR_DEFAULT;
+    if ((e[0] == '0' || e[0] == '1' || e[0] == '2') && e[1] == '\0') return e[0] - '0';
+    std::fprintf(stderr, "libfa_b200: FA_B200_TILED_D_PAIR=%s ignored (accepted: 0, 1, 2)\n", e);
+    return FA_TILED_D_PAIR_DEFAULT;
   }();
   return mode;
 }
 
+// The slab kernel, with its optional arguments (split ranges, causal, LSE, key padding, Lq != Lk).
+int dispatch_tiled_d_slab(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
+                          cudaStream_t s, const TiledDExtra& ex = TiledDExtra()) {
+  if (d == 256 && dtype == fa::DT_BF16) return launch_tiled_d<256, fa::DT_BF16>(Q, K, V, O, BH, L, s, ex);
+  if (d == 512 && dtype == fa::DT_BF16) return launch_tiled_d<512, fa::DT_BF16>(Q, K, V, O, BH, L, s, ex);
+  if (d == 256 && dtype == fa::DT_F16) return launch_tiled_d<256, fa::DT_F16>(Q, K, V, O, BH, L, s, ex);
+  if (d == 512 && dtype == fa::DT_F16) return launch_tiled_d<512, fa::DT_F16>(Q, K, V, O, BH, L, s, ex);
+  if (d == 128 && dtype == fa::DT_F32) return launch_tiled_d<128, fa::DT_F32>(Q, K, V, O, BH, L, s, ex);
+  if (d == 256 && dtype == fa::DT_F32) return launch_tiled_d<256, fa::DT_F32>(Q, K, V, O, BH, L, s, ex);
+  return fail(FA_ERR_UNSUPPORTED_D, "tiled-d kernel serves d in {256,512} for bf16/fp16 and d in {128,256} for fp32; got d=" + std::to_string(d) +
+                                        " dtype=" + std::to_string(dtype));
+}
+
+// Dense (Q,K,V)->O: the CTA-pair kernel where it wins (16-bit d = 512 by default), else the slab kernel.
 int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH, int L, int d, int dtype,
                      cudaStream_t s) {
   const int pair_mode = tiled_d_pair_mode();
@@ -271,15 +378,11 @@ int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int B
   if (pair_mode >= 1 && d == 512 && dtype == fa::DT_F16) return launch_tiled_d_pair<512, fa::DT_F16>(Q, K, V, O, BH, L, s);
   if (pair_mode >= 2 && d == 256 && dtype == fa::DT_BF16) return launch_tiled_d_pair<256, fa::DT_BF16>(Q, K, V, O, BH, L, s);
   if (pair_mode >= 2 && d == 256 && dtype == fa::DT_F16) return launch_tiled_d_pair<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
-  if (d == 256 && dtype == fa::DT_BF16) return launch_tiled_d<256, fa::DT_BF16>(Q, K, V, O, BH, L, s);
-  if (d == 512 && dtype == fa::DT_BF16) return launch_tiled_d<512, fa::DT_BF16>(Q, K, V, O, BH, L, s);
-  if (d == 256 && dtype == fa::DT_F16) return launch_tiled_d<256, fa::DT_F16>(Q, K, V, O, BH, L, s);
-  if (d == 512 && dtype == fa::DT_F16) return launch_tiled_d<512, fa::DT_F16>(Q, K, V, O, BH, L, s);
-  if (d == 128 && dtype == fa::DT_F32) return launch_tiled_d<128, fa::DT_F32>(Q, K, V, O, BH, L, s);
-  if (d == 256 && dtype == fa::DT_F32) return launch_tiled_d<256, fa::DT_F32>(Q, K, V, O, BH, L, s);
-  return fail(FA_ERR_UNSUPPORTED_D, "tiled-d kernel serves d in {256,512} for bf16/fp16 and d in {128,256} for fp32; got d=" + std::to_string(d) +
-                                        " dtype=" + std::to_string(dtype));
+  return dispatch_tiled_d_slab(Q, K, V, O, BH, L, d, dtype, s);
 }
+
+// Does the fused-tile kernel (K1) serve this (d, dtype)?  Otherwise the row is 512-1024 bytes and the slab kernel does.
+bool fused_tile_serves(int d, int dtype) { return d <= 128 && !(dtype == FA_DTYPE_F32 && d > 64); }
 
 template <int D, int DT>
 int launch_combine(const float* o_accum, const float* lse_accum, void* O, long long rows, int n_splits,
@@ -299,7 +402,8 @@ int launch_combine(const float* o_accum, const float* lse_accum, void* O, long l
   return FA_OK;
 }
 
-// cached device staging for the host-buffer entry point
+// Cached device staging for the host-buffer entry point: ONE set per device (buffers, streams and events belong to the
+// device they were created on), each behind its own mutex so host threads driving different GPUs do not serialise.
 struct HostStaging {
   void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t bytes = 0;
@@ -316,7 +420,22 @@ struct HostStaging {
   cudaEvent_t ev_h2d[kChunks] = {}, ev_comp[kChunks] = {};
   bool streams_ready = false;
   std::mutex mu;
-} g_stage;
+
+  void release_buffers() {
+    for (auto& b : buf) {
+      if (b) cudaFree(b);
+      b = nullptr;
+    }
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    bytes = ws_bytes = 0;
+  }
+  // Nothing of a failed call may still be in flight towards the caller's host buffers when the error is returned.
+  void drain() {
+    if (!streams_ready) return;
+    for (auto& st : stream) cudaStreamSynchronize(st);
+  }
+} g_stage[kMaxDevices];
 
 }  // namespace
 
@@ -345,7 +464,13 @@ int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float
   int rc = check_common(Q, K, V, O, B, H, L, d, dtype);
   if (rc != FA_OK) return rc;
   if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
-  if (d > 128) return fail(FA_ERR_UNSUPPORTED_D, "LSE output / causal masking are served by the fused-tile kernel only (d <= 128)");
+  if (!fused_tile_serves(d, dtype)) {
+    TiledDExtra tx;
+    tx.lse_out = LSE;
+    tx.causal = (flags & FA_FLAG_CAUSAL) ? 1 : 0;
+    if (tx.lse_out == nullptr && !tx.causal) return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, static_cast<cudaStream_t>(stream));
+    return dispatch_tiled_d_slab(Q, K, V, O, B * H, L, d, dtype, static_cast<cudaStream_t>(stream), tx);
+  }
   return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
                              LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0);
 }
@@ -357,12 +482,17 @@ int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, f
   if (Lk <= 0) return fail(FA_ERR_SHAPE, "Lk must be positive");
   if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
   if ((flags & FA_FLAG_CAUSAL) && Lq != Lk) return fail(FA_ERR_SHAPE, "causal masking needs Lq == Lk");
-  if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
-    return fail(FA_ERR_UNSUPPORTED_D, "key-padding / Lq != Lk are served by the fused-tile kernel only (row of at most 256 bytes)");
   FwdExtra ex;
   ex.Lk = Lk;
   ex.H = H;
   ex.kv_lens = kv_lens;
+  if (!fused_tile_serves(d, dtype)) {
+    TiledDExtra tx;
+    tx.lse_out = LSE;
+    tx.causal = (flags & FA_FLAG_CAUSAL) ? 1 : 0;
+    tx.fx = ex;
+    return dispatch_tiled_d_slab(Q, K, V, O, B * H, Lq, d, dtype, static_cast<cudaStream_t>(stream), tx);
+  }
   return dispatch_fwd<false>(Q, K, V, O, B * H, Lq, d, dtype, Lk, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
                              LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0, ex);
 }
@@ -380,14 +510,20 @@ int fa_partial_forward(const void* Q, const void* K, const void* V, float* Opart
       (out_head_rows != 0 && out_head_rows < Lq))
     return fail(FA_ERR_SHAPE, "head strides (in rows) must be 0 (dense) or at least the row count");
   if (out_head_rows > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "out_head_rows too large");
-  if (d > 128 || (dtype == FA_DTYPE_F32 && d > 64))
-    return fail(FA_ERR_UNSUPPORTED_D, "partial attention is served by the fused-tile kernel only (row of at most 256 bytes)");
   FwdExtra ex;
   ex.Lk = Lk;
   ex.H = H;
   ex.q_head_rows = q_head_rows;
   ex.kv_head_rows = kv_head_rows;
   ex.out_head_rows = out_head_rows;
+  if (!fused_tile_serves(d, dtype)) {
+    TiledDExtra tx;
+    tx.o_accum = Opartial;
+    tx.lse_accum = LSEpartial;
+    tx.causal = (flags & FA_FLAG_CAUSAL) ? 1 : 0;
+    tx.fx = ex;
+    return dispatch_tiled_d_slab(Q, K, V, nullptr, B * H, Lq, d, dtype, static_cast<cudaStream_t>(stream), tx);
+  }
   return dispatch_fwd<true>(Q, K, V, nullptr, B * H, Lq, d, dtype, /*kv_per_split=*/Lk, /*n_splits=*/1, Opartial,
                             LSEpartial, static_cast<cudaStream_t>(stream), nullptr, (flags & FA_FLAG_CAUSAL) ? 1 : 0, ex);
 }
@@ -400,8 +536,7 @@ int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, 
   if (d_tile_qk <= 0 || d_tile_v <= 0 || d % d_tile_qk != 0 || d % d_tile_v != 0)
     return fail(FA_ERR_SHAPE, "d_tile_qk and d_tile_v must be positive divisors of d");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (d <= 128 && !(dtype == FA_DTYPE_F32 && d > 64))
-    return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
+  if (fused_tile_serves(d, dtype)) return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, s);
   return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, s);
 }
 
@@ -439,6 +574,16 @@ int fa_v2_splitkv_forward(const void* Q, const void* K, const void* V, float* Oa
   if (kv_per_split <= 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
   if (LSEaccum == nullptr) return fail(FA_ERR_ALIGN, "LSEaccum must be non-null");
   const int ns = fa_v2_num_splits(L, kv_per_split);
+  if (!fused_tile_serves(d, dtype)) {
+    // rows of 512-1024 bytes (16-bit d = 256/512, fp32 d = 128/256 — the reference V2's own default D = 128 in its
+    // USE_FP64 mode): the slab tiled-d kernel with a key range per CTA
+    TiledDExtra tx;
+    tx.kv_per_split = kv_per_split;
+    tx.n_splits = ns;
+    tx.o_accum = Oaccum;
+    tx.lse_accum = LSEaccum;
+    return dispatch_tiled_d_slab(Q, K, V, nullptr, B * H, L, d, dtype, static_cast<cudaStream_t>(stream), tx);
+  }
   return dispatch_fwd<true>(Q, K, V, nullptr, B * H, L, d, dtype, kv_per_split, ns, Oaccum, LSEaccum,
                             static_cast<cudaStream_t>(stream));
 }
@@ -485,43 +630,52 @@ int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, i
 }
 
 void fa_release_host_staging(void) {
-  std::lock_guard<std::mutex> lk(g_stage.mu);
-  for (auto& b : g_stage.buf) {
-    if (b) cudaFree(b);
-    b = nullptr;
-  }
-  if (g_stage.ws) cudaFree(g_stage.ws);
-  g_stage.ws = nullptr;
-  g_stage.bytes = g_stage.ws_bytes = 0;
+  const int dev = current_device();
+  if (dev < 0) return;
+  HostStaging& st = g_stage[dev];
+  std::lock_guard<std::mutex> lk(st.mu);
+  st.drain();
+  st.release_buffers();
+}
+
+void fa_debug_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (hits) *hits = g_map_hits.load();
+  if (misses) *misses = g_map_misses.load();
 }
 
 int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh, void* Oh, int B, int H, int L, int d,
                     int kv_per_split, int dtype) {
+  // every argument is validated before anything is allocated or enqueued
   if (!Qh || !Kh || !Vh || !Oh) return fail(FA_ERR_ALIGN, "host pointers must be non-null");
   if (B <= 0 || H <= 0 || L <= 0 || d <= 0) return fail(FA_ERR_SHAPE, "B, H, L, d must be positive");
   if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_BF16 && dtype != FA_DTYPE_F16) return fail(FA_ERR_DTYPE, "unknown dtype");
-  std::lock_guard<std::mutex> lk(g_stage.mu);
+  if (variant < 0 || variant > 2) return fail(FA_ERR_SHAPE, "variant must be 0 (V1), 1 (tiled-d) or 2 (V2)");
+  if (variant == 2 && kv_per_split <= 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
+  const int dev = current_device();
+  if (dev < 0) return fail(FA_ERR_CUDA, "cannot query the current device");
+  HostStaging& S = g_stage[dev];
+  std::lock_guard<std::mutex> lk(S.mu);
   const size_t bytes = size_t(B) * H * L * d * elem_size(dtype);
-  if (bytes > g_stage.bytes) {
-    for (auto& b : g_stage.buf) {
+  if (bytes > S.bytes) {
+    S.drain();
+    for (auto& b : S.buf) {
       if (b) cudaFree(b);
       b = nullptr;
     }
-    g_stage.bytes = 0;
-    for (auto& b : g_stage.buf) FA_CUDA_TRY(cudaMalloc(&b, bytes));
-    g_stage.bytes = bytes;
+    S.bytes = 0;
+    for (auto& b : S.buf) FA_CUDA_TRY(cudaMalloc(&b, bytes));
+    S.bytes = bytes;
   }
-  if (variant < 0 || variant > 2) return fail(FA_ERR_SHAPE, "variant must be 0 (V1), 1 (tiled-d) or 2 (V2)");
   // Heads are independent, so the batch is pipelined in head chunks over three streams: while chunk c computes, chunk
   // c+1 is on the H2D copy engine and chunk c-1 on the D2H engine (PCIe is full duplex).  The reference drivers copy,
   // launch and copy back strictly in sequence (flash_attention_v1/CUDA/driver.cu:184-247).
-  if (!g_stage.streams_ready) {
-    for (auto& st : g_stage.stream) FA_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& e : g_stage.ev_h2d) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : g_stage.ev_comp) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    g_stage.streams_ready = true;
+  if (!S.streams_ready) {
+    for (auto& st : S.stream) FA_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : S.ev_h2d) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : S.ev_comp) FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    S.streams_ready = true;
   }
-  cudaStream_t s_h2d = g_stage.stream[0], s_comp = g_stage.stream[1], s_d2h = g_stage.stream[2];
+  cudaStream_t s_h2d = S.stream[0], s_comp = S.stream[1], s_d2h = S.stream[2];
   const int BH = B * H;
   // Chunk sizes halve (1/2, 1/4, ... of the heads, the last two equal): every cudaMemcpyAsync costs ~12 us of copy-
   // engine set-up, so few large copies up front, and a small last chunk so little D2H is left when the H2D stream ends.
@@ -544,32 +698,41 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
   for (int c = 1; c <= n_chunks; ++c) bounds[c] = int((long long)BH * c / n_chunks);
 #endif
   const size_t head_bytes = size_t(L) * d * elem_size(dtype);
-  size_t ws_need = 0;
   if (variant == 2) {
     int max_heads = 0;
     for (int c = 0; c < n_chunks; ++c) max_heads = std::max(max_heads, bounds[c + 1] - bounds[c]);
-    ws_need = fa_v2_workspace_bytes(1, max_heads, L, d, kv_per_split);
-    if (ws_need == 0) return fail(FA_ERR_SHAPE, "kv_per_split must be positive");
-    if (ws_need > g_stage.ws_bytes) {
-      if (g_stage.ws) cudaFree(g_stage.ws);
-      g_stage.ws = nullptr;
-      g_stage.ws_bytes = 0;
-      FA_CUDA_TRY(cudaMalloc(&g_stage.ws, ws_need));
-      g_stage.ws_bytes = ws_need;
+    const size_t ws_need = fa_v2_workspace_bytes(1, max_heads, L, d, kv_per_split);
+    if (ws_need > S.ws_bytes) {
+      S.drain();
+      if (S.ws) cudaFree(S.ws);
+      S.ws = nullptr;
+      S.ws_bytes = 0;
+      FA_CUDA_TRY(cudaMalloc(&S.ws, ws_need));
+      S.ws_bytes = ws_need;
     }
   }
+  // An error below leaves earlier chunks' copies in flight: drain the three streams before handing the error back.
+  auto bail = [&](int rc) {
+    S.drain();
+    return rc;
+  };
+#define FA_HOST_TRY(expr)                                                                                       \
+  do {                                                                                                          \
+    cudaError_t _e = (expr);                                                                                    \
+    if (_e != cudaSuccess) return bail(fail(FA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+  } while (0)
   for (int c = 0; c < n_chunks; ++c) {
     const int h0 = bounds[c], h1 = bounds[c + 1];
     const int nh = h1 - h0;
     if (nh == 0) continue;
     const size_t off = size_t(h0) * head_bytes, cb = size_t(nh) * head_bytes;
-    char *dQ = static_cast<char*>(g_stage.buf[0]) + off, *dK = static_cast<char*>(g_stage.buf[1]) + off;
-    char *dV = static_cast<char*>(g_stage.buf[2]) + off, *dO = static_cast<char*>(g_stage.buf[3]) + off;
-    FA_CUDA_TRY(cudaMemcpyAsync(dQ, static_cast<const char*>(Qh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
-    FA_CUDA_TRY(cudaMemcpyAsync(dK, static_cast<const char*>(Kh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
-    FA_CUDA_TRY(cudaMemcpyAsync(dV, static_cast<const char*>(Vh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
-    FA_CUDA_TRY(cudaEventRecord(g_stage.ev_h2d[c], s_h2d));
-    FA_CUDA_TRY(cudaStreamWaitEvent(s_comp, g_stage.ev_h2d[c], 0));
+    char *dQ = static_cast<char*>(S.buf[0]) + off, *dK = static_cast<char*>(S.buf[1]) + off;
+    char *dV = static_cast<char*>(S.buf[2]) + off, *dO = static_cast<char*>(S.buf[3]) + off;
+    FA_HOST_TRY(cudaMemcpyAsync(dQ, static_cast<const char*>(Qh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_HOST_TRY(cudaMemcpyAsync(dK, static_cast<const char*>(Kh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_HOST_TRY(cudaMemcpyAsync(dV, static_cast<const char*>(Vh) + off, cb, cudaMemcpyHostToDevice, s_h2d));
+    FA_HOST_TRY(cudaEventRecord(S.ev_h2d[c], s_h2d));
+    FA_HOST_TRY(cudaStreamWaitEvent(s_comp, S.ev_h2d[c], 0));
     int rc;
     if (variant == 0) {
       rc = fa_v1_forward(dQ, dK, dV, dO, 1, nh, L, d, dtype, s_comp);
@@ -577,17 +740,15 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
       const int dt = d >= 64 ? 64 : d;
       rc = fa_v1_tiled_d_forward(dQ, dK, dV, dO, 1, nh, L, d, dt, dt, dtype, s_comp);
     } else {
-      rc = fa_v2_forward(dQ, dK, dV, dO, 1, nh, L, d, kv_per_split, dtype, g_stage.ws, g_stage.ws_bytes, s_comp);
+      rc = fa_v2_forward(dQ, dK, dV, dO, 1, nh, L, d, kv_per_split, dtype, S.ws, S.ws_bytes, s_comp);
     }
-    if (rc != FA_OK) {
-      cudaDeviceSynchronize();
-      return rc;
-    }
-    FA_CUDA_TRY(cudaEventRecord(g_stage.ev_comp[c], s_comp));
-    FA_CUDA_TRY(cudaStreamWaitEvent(s_d2h, g_stage.ev_comp[c], 0));
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(Oh) + off, dO, cb, cudaMemcpyDeviceToHost, s_d2h));
+    if (rc != FA_OK) return bail(rc);
+    FA_HOST_TRY(cudaEventRecord(S.ev_comp[c], s_comp));
+    FA_HOST_TRY(cudaStreamWaitEvent(s_d2h, S.ev_comp[c], 0));
+    FA_HOST_TRY(cudaMemcpyAsync(static_cast<char*>(Oh) + off, dO, cb, cudaMemcpyDeviceToHost, s_d2h));
   }
-  FA_CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  FA_HOST_TRY(cudaStreamSynchronize(s_d2h));
+#undef FA_HOST_TRY
   return FA_OK;
 }
 

@@ -18,6 +18,11 @@
 //   smem  Q resident as D/64 swizzled [128 x 128 B] blocks; one ring of 16 KB stages streams, per KV tile,
 //         D/64 K chunks ([128 keys x 64 d], K-major B operand) then 4 V chunks ([128 keys x 64 d_v], MN-major B operand).
 //   warps 0-3 softmax (thread <-> row), 4 TMA producer, 5 MMA issuer.
+//
+// Beyond the reference's dense (Q,K,V)->O contract the kernel also serves, at run time (FwdParams), what the fused-tile
+// kernel does for d <= 128: a key range per CTA (V2 split-KV partials: fp32 rows normalised by the split's own row sum
+// + log-sum-exp, flash_attention_v2/CUDA/flash_attention_v2.h:243-341), Lq != Lk, key-padding lengths, causal masking
+// (KV tiles above the diagonal are never loaded) and the per-row log-sum-exp output.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -78,8 +83,15 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int slab = blockIdx.x % T::NSLAB;      // which 256-wide slab of the output head dim
   const int n_qtiles = (p.L + BM - 1) / BM;
   const int q_row0 = ((blockIdx.x / T::NSLAB) % n_qtiles) * BM;
-  const int bh = blockIdx.x / (T::NSLAB * n_qtiles);
-  const int n_tiles = (p.L + BN - 1) / BN;
+  const int hs = blockIdx.x / (T::NSLAB * n_qtiles);   // (head, split), split fastest
+  const int split = hs % p.n_splits;
+  const int bh = hs / p.n_splits;
+  int kv_len = p.Lk;
+  if (p.kv_lens != nullptr) kv_len = max(1, min(p.Lk, __ldg(p.kv_lens + bh / p.H)));   // key-padding mask
+  const int kv_begin = split * p.kv_per_split;
+  int kv_end = min(kv_len, kv_begin + p.kv_per_split);
+  if (p.causal) kv_end = min(kv_end, q_row0 + BM);   // nothing right of this q-tile's diagonal block is needed
+  const int n_tiles = (kv_end - kv_begin + BN - 1) / BN;
 
   if (warp == 5 && lane == 0) {
     mbar_init(q_full, 1);
@@ -124,11 +136,11 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         ++it;
       };
       // consumption order: K(0) | K(1) V(0) | K(2) V(1) | ... | V(n-1)
-      for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, 0);
+      for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, kv_begin);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles)
-          for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, (j + 1) * BN);
-        for (int v = 0; v < NVC; ++v) load_chunk(&tmV, slab * T::DV + v * CH, j * BN);
+          for (int c = 0; c < NKC; ++c) load_chunk(&tmK, c * CH, kv_begin + (j + 1) * BN);
+        for (int v = 0; v < NVC; ++v) load_chunk(&tmV, slab * T::DV + v * CH, kv_begin + j * BN);
       }
     }
   } else if (warp == 5) {
@@ -198,7 +210,9 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
       tc_wait_ld();
 
-      const int valid = p.L - j * BN;
+      // leading columns of this tile my row may attend to: the ragged end of the key range and, when causal, the diagonal
+      int valid = kv_end - (kv_begin + j * BN);
+      if (p.causal) valid = min(valid, q_row0 + row - j * BN + 1);
       if (valid < BN) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -281,6 +295,27 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
+    const int row_g = q_row0 + row;
+    if (slab == 0 && p.lse_out != nullptr && row_g < p.L) p.lse_out[size_t(bh) * p.L + row_g] = m_used * p.scale + __logf(l);
+    if (p.o_accum != nullptr) {
+      // split / partial epilogue: fp32 rows normalised by this key range's own row sum, plus its log-sum-exp
+      const size_t ridx = (size_t(split) * p.BH + bh) * p.out_head_rows + row_g;
+      if (slab == 0 && row_g < p.L) p.lse_accum[ridx] = m_used * p.scale + __logf(l);
+      float* dst = p.o_accum + ridx * D + slab * T::DV;
+#pragma unroll 1
+      for (int c = 0; c < T::DV / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tc_wait_ld();
+        if (row_g < p.L) {
+#pragma unroll
+          for (int x = 0; x < 32; x += 4)
+            *reinterpret_cast<float4*>(dst + c * 32 + x) =
+                make_float4(__uint_as_float(o[x]) * inv_l, __uint_as_float(o[x + 1]) * inv_l,
+                            __uint_as_float(o[x + 2]) * inv_l, __uint_as_float(o[x + 3]) * inv_l);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < T::DV / 32; ++c) {
       uint32_t o[32];
@@ -317,6 +352,7 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int b = 0; b < NVC; ++b) tma_store_3d(&tmO, sQ + b * BLK_BYTES, slab * T::DV + b * CH, q_row0, bh);
       tma_store_commit();
       tma_store_wait_all();
+    }
     }
   }
 

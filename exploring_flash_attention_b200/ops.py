@@ -25,6 +25,26 @@ def _prep(Q, K, V):
     return Q.contiguous(), K.contiguous(), V.contiguous()
 
 
+def _check_buffer(t, shape, dtype, device, what):
+    """Caller-supplied output / workspace buffers go to the C ABI as raw pointers: refuse anything the kernels would
+    write out of bounds (wrong shape, dtype, device, or a non-contiguous view)."""
+    if not isinstance(t, torch.Tensor):
+        raise _lib.FlashAttentionError(-1, f"{what} must be a torch tensor")
+    if t.device != device:
+        raise _lib.FlashAttentionError(-3, f"{what} is on {t.device}, expected {device}")
+    if t.dtype != dtype:
+        raise _lib.FlashAttentionError(-2, f"{what} has dtype {t.dtype}, expected {dtype}")
+    if tuple(t.shape) != tuple(shape):
+        raise _lib.FlashAttentionError(-1, f"{what} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    if not t.is_contiguous():
+        raise _lib.FlashAttentionError(-3, f"{what} must be contiguous")
+    return t
+
+
+def _out_like(O, Q, what="O"):
+    return torch.empty_like(Q) if O is None else _check_buffer(O, Q.shape, Q.dtype, Q.device, what)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -48,8 +68,7 @@ def flash_attention_v1(Q, K, V, O=None, sync: bool = False):
     """O = softmax(Q K^T / sqrt(d)) V for [B,H,L,d] tensors (fused-tile kernel, d <= 128)."""
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
-    if O is None:
-        O = torch.empty_like(Q)
+    O = _out_like(O, Q)
     lib = _lib.load()
     _lib.check(lib.fa_v1_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d, _DTYPES[Q.dtype],
                                  _stream()))
@@ -64,8 +83,7 @@ def flash_attention_v1_ex(Q, K, V, O=None, causal: bool = False, return_lse: boo
     log-sum-exp (natural log of sum_j exp(q.k_j/sqrt(d))). Returns O, or (O, LSE [B,H,L] fp32)."""
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
-    if O is None:
-        O = torch.empty_like(Q)
+    O = _out_like(O, Q)
     lse = torch.empty((B, H, L), dtype=torch.float32, device=Q.device) if return_lse else None
     lib = _lib.load()
     _lib.check(lib.fa_v1_forward_ex(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
@@ -98,8 +116,7 @@ def flash_attention_varlen(Q, K, V, kv_lens=None, O=None, causal: bool = False, 
     Q, K, V = _prep_rect(Q, K, V)
     B, H, Lq, d = Q.shape
     Lk = K.shape[2]
-    if O is None:
-        O = torch.empty_like(Q)
+    O = _out_like(O, Q)
     if kv_lens is not None:
         if kv_lens.dtype != torch.int32 or kv_lens.numel() != B or kv_lens.device != Q.device:
             raise _lib.FlashAttentionError(-1, "kv_lens must be an int32 tensor of B entries on Q's device")
@@ -163,8 +180,7 @@ def flash_attention_v1_tiled_d(Q, K, V, O=None, d_tile_qk: int = 32, d_tile_v: i
     """Tiled-d variant (head dims up to 512); d_tile_* are validated streaming hints."""
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
-    if O is None:
-        O = torch.empty_like(Q)
+    O = _out_like(O, Q)
     lib = _lib.load()
     _lib.check(lib.fa_v1_tiled_d_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d,
                                          d_tile_qk, d_tile_v, _DTYPES[Q.dtype], _stream()))
@@ -178,8 +194,7 @@ def flash_attention_v1_tiled_d_pair(Q, K, V, O=None, sync: bool = False):
     """Tiled-d on CTA pairs (fa_v1_tiled_d_pair_forward): bf16/fp16, d in {256, 512}."""
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
-    if O is None:
-        O = torch.empty_like(Q)
+    O = _out_like(O, Q)
     lib = _lib.load()
     _lib.check(lib.fa_v1_tiled_d_pair_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), B, H, L, d,
                                               _DTYPES[Q.dtype], _stream()))
@@ -207,6 +222,13 @@ def flash_attention_v2_splitkv(Q, K, V, kv_per_split: int, Oaccum=None, LSEaccum
     B, H, L, d = Q.shape
     if Oaccum is None or LSEaccum is None:
         Oaccum, LSEaccum = v2_workspace(B, H, L, d, kv_per_split, Q.device)
+    else:
+        # a reused workspace must hold exactly this call's splits: the kernel writes n_splits*B*H*L rows into it
+        S = v2_num_splits(L, kv_per_split)
+        if S <= 0:
+            raise _lib.FlashAttentionError(-1, "kv_per_split must be positive")
+        _check_buffer(Oaccum, (S, B * H, L, d), torch.float32, Q.device, "Oaccum")
+        _check_buffer(LSEaccum, (S, B * H, L), torch.float32, Q.device, "LSEaccum")
     lib = _lib.load()
     _lib.check(lib.fa_v2_splitkv_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), Oaccum.data_ptr(),
                                          LSEaccum.data_ptr(), B, H, L, d, kv_per_split, _DTYPES[Q.dtype], _stream()))
@@ -216,9 +238,21 @@ def flash_attention_v2_splitkv(Q, K, V, kv_per_split: int, Oaccum=None, LSEaccum
 @_on_device_of
 def flash_attention_v2_combine(Oaccum, LSEaccum, out_dtype, shape, O=None):
     B, H, L, d = shape
+    if not (isinstance(Oaccum, torch.Tensor) and Oaccum.is_cuda and Oaccum.dim() >= 1):
+        raise RuntimeError("flash-attention B200 path needs CUDA tensors: there is no CPU fallback")
+    if out_dtype not in _DTYPES:
+        raise _lib.FlashAttentionError(-2, f"unsupported dtype {out_dtype}")
     S = Oaccum.shape[0]
+    # [S,B*H,L,d] or any contiguous view with the same element count per split (e.g. [S,1,B*H*L,d])
+    if Oaccum.dtype != torch.float32 or not Oaccum.is_contiguous() or Oaccum.numel() != S * B * H * L * d:
+        raise _lib.FlashAttentionError(-1, f"Oaccum must be contiguous fp32 with {S}*{B * H * L * d} elements")
+    if (not isinstance(LSEaccum, torch.Tensor) or LSEaccum.dtype != torch.float32 or not LSEaccum.is_contiguous()
+            or LSEaccum.numel() != S * B * H * L or LSEaccum.device != Oaccum.device):
+        raise _lib.FlashAttentionError(-1, f"LSEaccum must be contiguous fp32 with {S}*{B * H * L} elements on Oaccum's device")
     if O is None:
         O = torch.empty((B, H, L, d), dtype=out_dtype, device=Oaccum.device)
+    else:
+        _check_buffer(O, (B, H, L, d), out_dtype, Oaccum.device, "O")
     lib = _lib.load()
     _lib.check(lib.fa_v2_combine(Oaccum.data_ptr(), LSEaccum.data_ptr(), O.data_ptr(), B, H, L, d, S,
                                  _DTYPES[out_dtype], _stream()))
@@ -244,9 +278,16 @@ def flash_attention_host(Qh, Kh, Vh, Oh=None, variant: int = 0, kv_per_split: in
     launchers (flash_attention_v1/CUDA/driver.cu:184-247). Tensors are CPU tensors, ideally pinned."""
     if Qh.is_cuda:
         raise RuntimeError("flash_attention_host takes host tensors")
+    if Qh.dim() != 4 or Qh.dtype not in _DTYPES:
+        raise _lib.FlashAttentionError(-1, "Qh must be a [B,H,L,d] host tensor of a supported dtype")
     B, H, L, d = Qh.shape
+    cpu = torch.device("cpu")
+    for t, what in ((Qh, "Qh"), (Kh, "Kh"), (Vh, "Vh")):
+        _check_buffer(t, Qh.shape, Qh.dtype, cpu, what)
     if Oh is None:
         Oh = torch.empty_like(Qh).pin_memory()
+    else:
+        _check_buffer(Oh, Qh.shape, Qh.dtype, cpu, "Oh")
     lib = _lib.load()
     _lib.check(lib.fa_forward_host(variant, Qh.data_ptr(), Kh.data_ptr(), Vh.data_ptr(), Oh.data_ptr(), B, H, L, d,
                                    kv_per_split, _DTYPES[Qh.dtype]))

@@ -57,7 +57,8 @@ int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, i
  * flash_attention_v1/README_v1.md:169).  Same kernel as fa_v1_forward plus:
  *   LSE   optional [B*H*L] fp32 output: log(sum_j exp(q_i.k_j / sqrt(d))) per query row (NULL to skip);
  *   flags FA_FLAG_CAUSAL: query row i attends to keys 0..i only (KV tiles above the diagonal are never loaded).
- * d <= 128 only. */
+ * Every (d, dtype) fa_v1_forward serves; rows of 512-1024 bytes (16-bit d = 256/512, fp32 d = 128/256) run on the slab
+ * tiled-d kernel when LSE or a flag is given. */
 #define FA_FLAG_CAUSAL 1u
 int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int L, int d,
                      int dtype, unsigned flags, void* stream);
@@ -66,7 +67,7 @@ int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float
  *   Q, O [B,H,Lq,d];  K, V [B,H,Lk,d];
  *   kv_lens optional device int32[B]: every head of batch entry b attends to its first kv_lens[b] keys only
  *           (values are clamped to [1, Lk]; NULL = all Lk keys).  KV tiles past the length are never loaded.
- *   FA_FLAG_CAUSAL needs Lq == Lk.  Rows of at most 256 bytes (the fused-tile kernel). */
+ *   FA_FLAG_CAUSAL needs Lq == Lk.  Every (d, dtype) fa_v1_forward serves. */
 int fa_v1_forward_varlen(const void* Q, const void* K, const void* V, void* O, float* LSE, const int* kv_lens, int B,
                          int H, int Lq, int Lk, int d, int dtype, unsigned flags, void* stream);
 
@@ -93,7 +94,8 @@ int fa_v1_tiled_d_forward(const void* Q, const void* K, const void* V, void* O, 
 
 /* The same contract served by the CTA-pair kernel (two SMs share one 128-row query tile through 2-CTA tensor-core
  * MMAs, so no score tile is computed twice at d = 512): 16-bit dtypes, d in {256, 512}.  fa_v1_tiled_d_forward
- * routes to it when the environment variable FA_B200_TILED_D_PAIR is 1 (d = 512) or 2 (d = 256 as well). */
+ * routes 16-bit d = 512 to it BY DEFAULT (environment variable FA_B200_TILED_D_PAIR: 1 = the default, 2 = d = 256 as
+ * well, 0 = never: the single-CTA slab kernel; any other value is ignored with a warning). */
 int fa_v1_tiled_d_pair_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d,
                                int dtype, void* stream);
 
@@ -106,7 +108,9 @@ int fa_v1_tiled_d_pair_forward(const void* Q, const void* K, const void* V, void
  *   Oaccum   [n_splits][B*H][L][d]  each split normalised by its own l
  *   LSEaccum [n_splits][B*H][L]     m/sqrt(d) + ln(l)
  * which carries the same information as the reference's (O_unnormalised, m, l) triple
- * (flash_attention_v2.h:321-340). */
+ * (flash_attention_v2.h:321-340).  Every (d, dtype) fa_v1_forward serves: rows of at most 256 bytes on the fused-tile
+ * kernel, 16-bit d = 256/512 and fp32 d = 128/256 (the reference V2's default D = 128 in USE_FP64 mode) on the slab
+ * tiled-d kernel. */
 int fa_v2_num_splits(int L, int kv_per_split);
 size_t fa_v2_workspace_bytes(int B, int H, int L, int d, int kv_per_split);
 int fa_v2_splitkv_forward(const void* Q, const void* K, const void* V, float* Oaccum, float* LSEaccum, int B, int H,
@@ -123,7 +127,12 @@ int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, i
  * library between calls.  variant: 0 = V1, 1 = tiled-d, 2 = V2 (kv_per_split used).  Synchronous. */
 int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh, void* Oh, int B, int H, int L, int d,
                     int kv_per_split, int dtype);
-void fa_release_host_staging(void);
+void fa_release_host_staging(void);   /* frees the CURRENT device's staging buffers (one cached set per device) */
+
+/* Diagnostics: how many TMA tensor maps were served from the per-thread cache / had to be encoded by the driver since
+ * the library was loaded (launching on the same buffers step after step must not re-encode; the reference re-derives
+ * its launch state on every call, flash_attention_v1.h:280-292).  Either pointer may be NULL. */
+void fa_debug_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 #ifdef __cplusplus
 }

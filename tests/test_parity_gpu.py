@@ -330,11 +330,16 @@ def test_causal_and_lse_match_extended_oracle(ops, B, H, L, d, dtype):
     assert (O[:, :, 0].float() - V[:, :, 0].float()).abs().max().item() <= (1e-3 if dtype == torch.float32 else 1e-6)
 
 
-def test_causal_rejects_large_head_dim(ops):
+def test_unsupported_head_dims_are_refused_everywhere(ops):
+    """d outside {32,64,128,256,512} (and fp32 d = 512) has no kernel: every entry point says so, none falls back."""
     from exploring_flash_attention_b200 import FlashAttentionError
-    Q, K, V = uniform_qkv(1, 1, 128, 256, torch.bfloat16)
-    with pytest.raises(FlashAttentionError):
-        ops.flash_attention_v1_ex(Q, K, V, causal=True)
+    for d, dtype in ((48, torch.bfloat16), (1024, torch.bfloat16), (512, torch.float32)):
+        Q, K, V = uniform_qkv(1, 1, 128, d, dtype)
+        for call in (lambda: ops.flash_attention_v1_ex(Q, K, V, causal=True), lambda: ops.flash_attention_varlen(Q, K, V),
+                     lambda: ops.flash_attention_partial(Q, K, V), lambda: ops.flash_attention_v2(Q, K, V, 64)):
+            with pytest.raises(FlashAttentionError) as ei:
+                call()
+            assert ei.value.code == -4
 
 
 def test_v2_reference_signature_kernels_driver_loop(ops, golden):
@@ -473,13 +478,8 @@ def test_partial_causal_and_row_windows(ops, dtype, d):
         ops.flash_attention_partial(Q.transpose(1, 2), K.transpose(1, 2), V.transpose(1, 2))
 
 
-def test_varlen_and_partial_reject_unsupported(ops):
+def test_varlen_rejects_bad_arguments(ops):
     from exploring_flash_attention_b200 import FlashAttentionError
-    Q = torch.zeros((1, 1, 128, 256), dtype=torch.bfloat16, device="cuda")
-    with pytest.raises(FlashAttentionError):
-        ops.flash_attention_varlen(Q, Q, Q)
-    with pytest.raises(FlashAttentionError):
-        ops.flash_attention_partial(Q, Q, Q)
     q = torch.zeros((1, 1, 128, 64), dtype=torch.bfloat16, device="cuda")
     k = torch.zeros((1, 1, 256, 64), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(FlashAttentionError):

@@ -41,6 +41,17 @@ def flops(B, H, L, d):
     return 4.0 * B * H * L * L * d
 
 
+def bench_config(workload, strong=False, world=1):
+    """The `config` object of the JSON line — identical in both arms (ours and --impl reference) by construction."""
+    B, H, L, d, dt, desc = WORKLOADS[workload]
+    tensor_bytes = B * H * L * d * (4 if dt == "f32" else 2) // (world if strong else 1)
+    nsets = 3 if tensor_bytes * 4 < (1 << 30) else 1
+    return {"workload": desc, "B": B, "H": H, "L": L, "d": d,
+            "per_gpu_batch": f"1/{world} of the {B * H} heads" if strong else f"B{B} H{H}",
+            "sharding": "independent (batch,head) work per GPU, no collective",
+            "l2": f"GPU arm: {nsets} rotating input sets, {4 * tensor_bytes * nsets / 1e6:.0f} MB working set > 126 MB L2, no flush"}
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -108,17 +119,6 @@ def nvml_index(local_rank):
     return local_rank
 
 
-def time_steps(fn, steps, torch):
-    """CUDA events on the launching (current) stream around exactly `steps` calls."""
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        fn(i)
-    e1.record()
-    e1.synchronize()
-    return e0.elapsed_time(e1)  # ms
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -167,6 +167,7 @@ def run_ours(args):
         q, k, v = ((torch.rand((Bl, Hl, L, d), generator=g, dtype=torch.float32) * 2 - 1).to(dtype).cuda() for _ in range(3))
         sets.append((q, k, v, torch.empty_like(q)))
     variant = 1 if args.workload in ("c2", "c5") else 0
+    launches = [0]
 
     def step(i):
         q, k, v, o = sets[i % nsets]
@@ -174,46 +175,62 @@ def run_ours(args):
             ops.flash_attention_v1_tiled_d(q, k, v, o, d_tile_qk=32, d_tile_v=32)
         else:
             ops.flash_attention_v1(q, k, v, o)
+        launches[0] += 1      # one kernel of ours per step (fa_fwd_kernel / fa_tiled_d[_pair]_kernel), nothing else
 
+    K = args.steps
     sampler = ClockSampler(nvml_index(local_rank)) if rank == 0 else None
     for i in range(max(args.warmup, 3)):
         step(i)
+    # calibration (untimed): how many blocks of K steps make the timed region at least MIN_REGION_MS long, so that the
+    # clock samples come from the timed region itself and a max-over-ranks is not the jitter of a 2 ms window
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(K):
+        step(i)
+    c1.record()
+    c1.synchronize()
+    est_block_ms = max_over_ranks(c0.elapsed_time(c1))
+    MIN_REGION_MS = 60.0
+    R = max(1, min(2000, int(-(-MIN_REGION_MS // max(est_block_ms, 1e-3)))))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
     barrier()
+    launches[0] = 0
     if sampler:
         sampler.start()
-    ms_total = time_steps(step, args.steps, torch)
+    ev[0].record()
+    for r in range(R):          # R blocks of EXACTLY K steps, back to back on the launching (current) stream
+        for i in range(K):
+            step(r * K + i)
+        ev[r + 1].record()
+    ev[R].synchronize()
     barrier()
     if sampler:
         sampler.pause()
-    ms_total = max_over_ranks(ms_total)
-    ms_step = ms_total / args.steps
+    gpu_launches = launches[0]
+    block_ms = [ev[r].elapsed_time(ev[r + 1]) for r in range(R)]
+    ms_total = max_over_ranks(ev[0].elapsed_time(ev[R]))
+    ms_step = ms_total / (R * K)                       # the bench value: whole timed region, max over ranks
+    ms_step_median_block = max_over_ranks(statistics.median(block_ms)) / K
     value = total_flops / (ms_step * 1e-3) / 1e12
-    clock_note = "sampled during the timed region"
-    if sampler and len(sampler.samples) < 5:
-        # timed region too short for NVML polling: replay the same step for ~0.4 s (untimed) and sample under that load
-        sampler.start()
-        t_end = time.time() + 0.4
-        i = 0
-        while time.time() < t_end:
-            for _ in range(20):
-                step(i)
-                i += 1
-            torch.cuda.synchronize()
-        sampler.pause()
-        clock_note = "timed region shorter than the NVML polling period; sampled during an untimed replay of the same step"
+    clock_note = f"sampled during the timed region ({ms_total:.0f} ms)"
 
     # ---- roofline of the dominant kernel (the one fused forward kernel per step), timed live on its stream
     # one kernel launch per step, launches back to back on one stream: the kernel's average duration over the timed
-    # region IS ms_step (a second timing pass after the clock-sampling replay would run power-capped and read lower)
+    # region IS ms_step
     per_launch_ms = ms_step
     achieved = flops(Bl, Hl, L, d) / (per_launch_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0),
-                "unit": "TFLOP/s", "frac": round(achieved / (pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0)), 4),
-                "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "kernel": "fa_fwd_kernel" if d <= 128 else ("fa_tiled_d_pair_kernel" if d == 512 and dt != "f32" else "fa_tiled_d_kernel"),
+    peak = pk["bf16_tflops"] / (2.0 if dt == "f32" else 1.0)
+    traffic = NCU_TRAFFIC_BYTES.get(args.workload, {})
+    roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic.get("bytes"), "traffic_source": traffic.get("source"),
+                "kernel": "fa_fwd_kernel" if d <= 128 else ("fa_tiled_d_pair_kernel" if d == 512 and dt != "f32" else "fa_tiled_d_kernel"),
                 "peak_source": pk["source"] + (", burst bf16 cuBLAS" if dt != "f32" else ", burst bf16 cuBLAS / 2 (tf32)"),
                 "frac_of_sustained": round(achieved / (pk["bf16_tflops_sustained"] / (2.0 if dt == "f32" else 1.0)), 4)
                 if pk["bf16_tflops_sustained"] else None,
-                "algorithmic_flops_per_launch": flops(Bl, Hl, L, d)}
+                "algorithmic_flops_per_launch": flops(Bl, Hl, L, d),
+                "algorithmic_bytes_per_launch": 4 * tensor_bytes}
 
     # ---- end to end through the C ABI with HOST buffers (H2D x3 + kernel + D2H inside the timed region)
     qh, kh, vh = (t.cpu().pin_memory() for t in sets[0][:3])
@@ -228,24 +245,60 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     barrier()
+    # the PCIe floor of the same step on this box, ALL ranks copying at once: the three inputs host->device on one
+    # stream while the output goes device->host on another (full duplex), no kernel.  e2e_ms / pcie_floor_ms says how
+    # much of the end-to-end time is the host link (shared by the ranks) rather than this library.
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dq, dk, dv, do = sets[0]
+
+    def copies():
+        with torch.cuda.stream(s_in):
+            dq.copy_(qh, non_blocking=True)
+            dk.copy_(kh, non_blocking=True)
+            dv.copy_(vh, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            oh.copy_(do, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copies()
+    floor_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    barrier()
     e2e = {"value": round(total_flops / (e2e_ms * 1e-3) / 1e12, 3), "unit": UNIT,
            "h2d_bytes_per_step": 3 * tensor_bytes, "d2h_bytes_per_step": tensor_bytes, "ms_per_step": round(e2e_ms, 3),
-           "steps": e2e_steps, "api": "fa_forward_host (include/fa_b200.h)"}
+           "steps": e2e_steps, "api": "fa_forward_host (include/fa_b200.h)",
+           "pcie_floor_ms": round(floor_ms, 3),
+           "pcie_floor_note": f"H2D of the 3 inputs + D2H of the output on two streams, no kernel, all {world} rank(s) at once "
+                              f"(max over ranks): {3 * tensor_bytes / floor_ms / 1e6:.1f} GB/s in per GPU; the library's "
+                              f"step is {e2e_ms / floor_ms:.2f}x this floor"}
+    del qh, kh, vh, oh, sets
+
+    also = {}
+    if args.also:
+        # every rank takes part (C4 heads are sharded over the ranks; the ring needs all of them); rank 0 reports
+        also["c4_strong"] = c4_strong(torch, dist, ops, pk, rank, world, max_over_ranks, barrier)
+        if world > 1:
+            also["ring"] = ring_checks(torch, dist, ops, rank, world, max_over_ranks, barrier)
+        elif rank == 0:
+            also.update(side_measurements(torch, ops, pk))
 
     out = None
     if rank == 0:
-        also = {}
-        if args.also and world == 1:
-            also = side_measurements(torch, ops, pk)
         cpu_base = cpu_baseline(args.workload) if world == 1 else None
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": dt, "data": "synthetic U[-1,1) seed 42 (random Q,K,V; no weights on this path)",
-            "config": {"workload": desc, "B": B, "H": H, "L": L, "d": d, "per_gpu_batch": f"{Bl * Hl} of {B * H} heads" if strong else f"B{B} H{H}",
-                       "sharding": "independent (batch,head) work per GPU, no collective",
-                       "l2": f"{nsets} rotating input sets, {4 * tensor_bytes * nsets / 1e6:.0f} MB working set > 126 MB L2, no flush"},
-            "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
+            "config": bench_config(args.workload, strong, world),
+            "timing": {"repeats": R, "timed_steps": R * K, "timed_region_ms": round(ms_total, 3),
+                       "ms_per_step_median_block": round(ms_step_median_block, 5),
+                       "note": f"{R} back-to-back blocks of exactly {K} steps inside ONE barrier+synchronize bracket (>= {MIN_REGION_MS:.0f} ms so "
+                               "clocks are sampled in the timed region); ms_per_step = whole region / timed_steps, max over ranks"},
+            "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_base,
             "clocks": sampler.result(clock_note) if sampler else None,
         }
         if also:
@@ -257,13 +310,136 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
 
 
+def c4_strong(torch, dist, ops, pk, rank, world, max_over_ranks, barrier):
+    """BASELINE.json configs[3] at every N: B8 H32 L16384 d128 bf16, the 256 heads sharded over the ranks by
+    sharding.head_range (the reference's independent grid rows, flash_attention_v1.h:170-172), no collective.
+    Whole-job TFLOP/s = 4*B*H*L^2*d / max-over-ranks time; per-rank roofline fraction; and, outside the timed region, a
+    sampled-row check of rank 0's output against the float64 oracle (the checker, oracle/reference.py)."""
+    try:
+        from exploring_flash_attention_b200.sharding import head_range
+        B, H, L, d = 8, 32, 16384, 128
+        hb, he = head_range(B * H, rank, world)
+        nh = he - hb
+        g = torch.Generator(device="cuda").manual_seed(4242 + rank)
+        q, k, v = ((torch.rand((1, nh, L, d), generator=g, device="cuda") * 2 - 1).bfloat16() for _ in range(3))
+        o = torch.empty_like(q)
+        for _ in range(2):
+            ops.flash_attention_v1(q, k, v, o)
+        barrier()
+        n = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            ops.flash_attention_v1(q, k, v, o)
+        e1.record()
+        e1.synchronize()
+        barrier()
+        my_ms = e0.elapsed_time(e1) / n
+        ms = max_over_ranks(my_ms)
+        tf = flops(B, H, L, d) / (ms * 1e-3) / 1e12
+        per_rank_tf = flops(1, nh, L, d) / (my_ms * 1e-3) / 1e12
+        res = {"workload": "B8 H32 L16384 d128 bf16, heads sharded", "n_gpus": world, "heads_per_rank": nh, "steps": n,
+               "ms": round(ms, 3), "tflops": round(tf, 1), "scaling": "strong",
+               "rank0_tflops": round(per_rank_tf, 1), "rank0_roofline_frac": round(per_rank_tf / pk["bf16_tflops"], 4),
+               "rank0_frac_of_sustained": round(per_rank_tf / pk["bf16_tflops_sustained"], 4) if pk["bf16_tflops_sustained"] else None,
+               "frac_of_nominal_2250_per_gpu": round(tf / world / 2250.0, 4)}
+        if rank == 0:
+            import numpy as np
+            from oracle import reference          # checker only, untimed
+            heads = sorted({0, nh // 2, nh - 1})
+            rows = np.r_[0:16, L // 2:L // 2 + 16, L - 16:L]
+            f = lambda x: x[0, heads].float().cpu().numpy()
+            ref = reference.naive_attention_batched_f64(f(q), f(k), f(v), rows=rows)
+            got = o[0, heads][:, rows].float().cpu().numpy()
+            res["max_abs_err"] = float(np.abs(got - ref).max())
+            res["max_abs_err_note"] = f"{len(heads)} heads x {len(rows)} rows of rank 0's shard vs the float64 oracle; tolerance 2e-3"
+        del q, k, v, o
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
+
+
+def ring_checks(torch, dist, ops, rank, world, max_over_ranks, barrier):
+    """N > 1 only, outside the bench value: (1) parity of the sequence-sharded path (sharding.ring_attention, both
+    transports, dense and causal zig-zag) and of gather_heads against the float64 oracle on a small case; (2) the C4
+    problem sequence-sharded over the ring, timed beside the head-sharded figure."""
+    import numpy as np
+    res = {}
+    try:
+        from exploring_flash_attention_b200 import sharding
+        from oracle import reference              # checker only, untimed
+        B, H, d = 1, 2, 128
+        Ls = 256
+        L = Ls * world
+        g = torch.Generator(device="cpu").manual_seed(77)        # same full tensors on every rank
+        Qf, Kf, Vf = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
+        f64 = lambda x: x.float().numpy().reshape(B * H, L, d)
+        errs = {}
+        for causal in (False, True):
+            ref = np.stack([reference.naive_attention_ex_f64(f64(Qf)[i], f64(Kf)[i], f64(Vf)[i], causal=causal)[0] for i in range(B * H)])
+            if causal:
+                mine = [sharding.zigzag_shard(x, rank, world).cuda().contiguous() for x in (Qf, Kf, Vf)]
+                ref_mine = sharding.zigzag_shard(torch.from_numpy(ref), rank, world).numpy()
+            else:
+                mine = [x[:, :, rank * Ls:(rank + 1) * Ls].cuda().contiguous() for x in (Qf, Kf, Vf)]
+                ref_mine = ref[:, rank * Ls:(rank + 1) * Ls]
+            for transport in ("nccl", "peer"):
+                try:
+                    O = sharding.ring_attention(*mine, transport=transport, causal=causal)
+                    torch.cuda.synchronize()
+                    err = float(np.abs(O.float().cpu().numpy().reshape(B * H, -1, d) - ref_mine).max())
+                except Exception as e:  # noqa: BLE001
+                    err = float("nan")
+                    res[f"error_{transport}_{'causal' if causal else 'dense'}"] = str(e)[:200]
+                errs[f"{transport}_{'causal' if causal else 'dense'}"] = max_over_ranks(err)
+        res["max_abs_err"] = errs
+        res["max_abs_err_note"] = f"B{B} H{H} L{L} d{d} bf16, every rank's rows vs the float64 oracle, max over ranks; tolerance 2e-3 (x2 on early causal rows)"
+        # gather_heads: head-sharded outputs assembled over NCCL equal the single-GPU output
+        Q8, K8, V8 = (x.expand(B, 8 * H, L, d).contiguous() for x in (Qf, Kf, Vf))
+        local = [sharding.shard_heads(x, rank, world).cuda().contiguous() for x in (Q8, K8, V8)]
+        O_local = ops.flash_attention_v1(*local)
+        O_all = sharding.gather_heads(O_local, 8 * H * B)
+        O_one = ops.flash_attention_v1(Q8.cuda(), K8.cuda(), V8.cuda())
+        res["gather_heads_bit_equal"] = bool(torch.equal(O_all.reshape(O_one.shape), O_one))
+    except Exception as e:  # noqa: BLE001
+        res["parity_error"] = str(e)[:300]
+    try:
+        from exploring_flash_attention_b200 import sharding
+        B, H, L, d = 8, 32, 16384, 128
+        Ls = L // world
+        g = torch.Generator(device="cuda").manual_seed(99 + rank)
+        q, k, v = ((torch.rand((B, H, Ls, d), generator=g, device="cuda") * 2 - 1).bfloat16() for _ in range(3))
+        timings = {}
+        for causal in (False, True):
+            for _ in range(2):
+                sharding.ring_attention(q, k, v, transport="peer", causal=causal)
+            barrier()
+            n = 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                sharding.ring_attention(q, k, v, transport="peer", causal=causal)
+            e1.record()
+            e1.synchronize()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1) / n)
+            fl = flops(B, H, L, d) * (0.5 if causal else 1.0)
+            timings["causal" if causal else "dense"] = {"ms": round(ms, 3), "tflops": round(fl / (ms * 1e-3) / 1e12, 1)}
+        res["c4_sequence_sharded_peer_transport"] = timings
+    except Exception as e:  # noqa: BLE001
+        res["ring_c4_error"] = str(e)[:300]
+    return res
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/)
-NCU_TRAFFIC_BYTES: dict = {"c2": 243_684_096}   # profiles/r1_fwd_c2_persistent_full.txt: 201.45 MB read + 42.24 MB written
+NCU_TRAFFIC_BYTES: dict = {
+    "c2": {"bytes": 243_684_096, "source": "profiles/r1_fwd_c2_persistent_full.txt (201.45 MB read + 42.24 MB written)"},
+}
 
 
 def side_measurements(torch, ops, pk):
-    """Other BASELINE.json configs, reported beside the headline (not the bench value): C4 long sequence, C5 d=512,
-    C1 tf32, C3 split-KV + combine with the combine kernel's HBM roofline."""
+    """Other BASELINE.json configs, reported beside the headline (not the bench value): C5 d=512, C1 tf32, C3 split-KV +
+    combine with the combine kernel's HBM roofline.  (C4 is c4_strong, run at every N.)"""
     res = {}
 
     def timed(fn, n, warm=3):
@@ -280,19 +456,6 @@ def side_measurements(torch, ops, pk):
 
     g = torch.Generator(device="cpu").manual_seed(7)
     mk = lambda B, H, L, d, dtype: tuple((torch.rand((B, H, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
-    try:
-        B, H, L, d = 8, 32, 16384, 128
-        q, k, v = mk(1, 32, L, d, torch.bfloat16)          # generate one batch row, tile it to B=8 (host RNG is slow)
-        q, k, v = (x.expand(B, H, L, d).contiguous() for x in (q, k, v))
-        o = torch.empty_like(q)
-        ms = timed(lambda: ops.flash_attention_v1(q, k, v, o), 5, warm=2)
-        tf = flops(B, H, L, d) / (ms * 1e-3) / 1e12
-        res["c4_B8_H32_L16384_d128_bf16"] = {"ms": round(ms, 3), "tflops": round(tf, 1),
-                                            "frac_of_measured_bf16_peak": round(tf / pk["bf16_tflops"], 4),
-                                            "frac_of_nominal_2250": round(tf / 2250.0, 4)}
-        del q, k, v, o
-    except Exception as e:  # noqa: BLE001
-        res["c4_error"] = str(e)[:200]
     try:
         B, H, L, d = 16, 8, 4096, 512                      # configs[4]: tiled-d on CTA pairs (fa_tiled_d_pair_kernel)
         q, k, v = mk(1, H, L, d, torch.bfloat16)
@@ -448,10 +611,13 @@ def run_reference(args):
     B, H, L, d, dt, desc = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     per_head_gflop = flops(1, 1, L, d) / 1e9
-    # bounded sample per step (~10 s of CPU work at ~1 GFLOP/s/thread), at most the whole batch, at least one head/thread
-    heads = int(min(B * H, max(threads, 10.0 * threads / max(per_head_gflop, 1e-3))))
+    # --steps / --warmup are honoured as given; each step is a bounded sample of the workload (a number of heads of the
+    # same shape, at least one per thread) sized so that the whole run, warm-up included, is ~90 s of CPU work at the
+    # ~1 GFLOP/s/thread the reference path reaches
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    per_step_s = 90.0 / (steps + warm)
+    heads = int(min(B * H, max(threads, per_step_s * threads / max(per_head_gflop, 1e-3))))
     heads = int(os.environ.get("FA_BENCH_CPU_HEADS", heads))       # test hook: shrink the CPU sample
-    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
     for _ in range(warm):
         cpu_sample(args.workload, heads, threads)
     secs, kind = [], "port"
@@ -466,8 +632,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(tf, 5), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warm, "ms_per_step": round(s * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 storage / f32 math", "data": "synthetic U[-1,1) seed 42",
-        "config": {"workload": desc, "B": B, "H": H, "L": L, "d": d, "sample_heads": heads},
-        "cpu_baseline": {"value": round(tf, 5), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "config": bench_config(args.workload, False, world),
+        "cpu_baseline": {"value": round(tf, 5), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "sample_heads": heads},
         "e2e": {"value": round(tf, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)

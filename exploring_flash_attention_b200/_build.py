@@ -14,6 +14,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = Path(os.environ["FA_B200_LIB"]) if os.environ.get("FA_B200_LIB") else CSRC / "libfa_b200.so"
 SOURCES = ["fa_api.cu"]
 HEADERS = ["sm100_ptx.cuh", "fa_fwd_sm100.cuh", "fa_tiled_d_sm100.cuh", "fa_tiled_d_pair_sm100.cuh", "fa_combine_sm100.cuh",
+           "fa_naive_sm100.cuh",
            "../../include/fa_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,6 +52,26 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
     if verbose:
         print(res.stderr)
     return target
+
+
+CONSUMER_SRC = CSRC.parents[1] / "tests" / "drivers" / "driver_v1.cu"
+CONSUMER_BIN = CONSUMER_SRC.with_suffix("")
+
+
+def build_consumer(force: bool = False) -> Path:
+    """Compile tests/drivers/driver_v1.cu — a C++ program that includes include/fa_b200.h and links -lfa_b200, the way a
+    reference driver.cu would after INTEGRATION.md §1 (it proves the header compiles as C++ and the ABI links)."""
+    build()
+    newest = max(CONSUMER_SRC.stat().st_mtime, (CSRC / "../../include/fa_b200.h").stat().st_mtime)
+    if not force and CONSUMER_BIN.exists() and CONSUMER_BIN.stat().st_mtime > newest:
+        return CONSUMER_BIN
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-I", str(CSRC / "../../include"),
+           str(CONSUMER_SRC), "-L", str(CSRC), "-lfa_b200", "-Xlinker", "-rpath", "-Xlinker",
+           "$ORIGIN/../../exploring_flash_attention_b200/csrc", "-o", str(CONSUMER_BIN)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return CONSUMER_BIN
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ from pathlib import Path
 
 from ._build import LIB_PATH
 
-FA_DTYPE_F32, FA_DTYPE_BF16, FA_DTYPE_F16 = 0, 1, 2
+FA_DTYPE_F32, FA_DTYPE_BF16, FA_DTYPE_F16, FA_DTYPE_F64 = 0, 1, 2, 3
 FA_OK = 0
 ERROR_NAMES = {-1: "FA_ERR_SHAPE", -2: "FA_ERR_DTYPE", -3: "FA_ERR_ALIGN", -4: "FA_ERR_UNSUPPORTED_D",
                -5: "FA_ERR_CUDA", -6: "FA_ERR_WORKSPACE"}
@@ -30,6 +30,8 @@ SYMBOLS = {
     "fa_v2_splitkv_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "fa_v2_combine": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "fa_v2_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "fa_naive_attention_workspace_bytes": (c_size_t, [c_int] * 4),
+    "fa_naive_attention": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "fa_forward_host": (c_int, [c_int] + [c_void_p] * 4 + [c_int] * 6),
     "fa_release_host_staging": (None, []),
     "fa_debug_map_cache_stats": (None, [c_void_p, c_void_p]),

@@ -2,9 +2,12 @@
 AssertionError behaviour (common/reference.py:7-21, :24-78, :81-96).
 
 `check_accuracy` / `print_comparison` are host-side validation logic restated from the reference.
-`naive_attention` keeps its (Q,K,V)->O contract for one [L,d] head but is evaluated on the GPU by the fused-tile
-kernel through the C ABI — this package has no CPU compute path.  (The float64 CPU oracle the tests judge against
-lives in oracle/, outside the package.)
+`naive_attention` keeps its (Q,K,V)->O contract for one [L,d] head and stays what it is in the reference — the thing
+the kernels are compared WITH: it runs fa_naive_attention (csrc/fa_naive_sm100.cuh), which materialises the [L,L] score
+matrix and evaluates reference.py:16-21 step by step on the CUDA cores in fp32 (float16 / float32 buffers) or fp64
+(float64 buffers, like the reference's own float64 runs).  It shares no code, no tensor-core path and no online-softmax
+recurrence with the fused kernels, and accepts any head dim.  This package has no CPU compute path; the float64 CPU
+oracle the tests judge against lives in oracle/, outside the package.
 """
 from __future__ import annotations
 
@@ -12,13 +15,18 @@ import numpy as np
 
 
 def naive_attention(Q, K, V):
-    """softmax(Q K^T / sqrt(d)) V for [L,d] NumPy arrays; returns [L,d] in Q's dtype. Runs on the current CUDA device."""
+    """softmax(Q K^T / sqrt(d)) V for [L,d] NumPy arrays; returns [L,d] in Q's dtype. Runs on the current CUDA device,
+    independently of the fused kernels (materialised scores, fp32 / fp64 CUDA-core math)."""
+    import torch
+
     from .. import ops
-    from .._numpy_bridge import to_device_head
-    L, d = Q.shape
-    q, k, v = (to_device_head(x, L, d) for x in (Q, K, V))
-    O = ops.flash_attention_v1(q, k, v, sync=True)
-    return O.reshape(L, d).float().cpu().numpy().astype(np.asarray(Q).dtype)
+    from .._numpy_bridge import require_cuda
+    dev = require_cuda()
+    Qa = np.asarray(Q)
+    compute = torch.float64 if Qa.dtype == np.float64 else torch.float32
+    q, k, v = (torch.from_numpy(np.ascontiguousarray(np.asarray(x))).to(dev, dtype=compute) for x in (Q, K, V))
+    O = ops.naive_attention_reference(q, k, v)
+    return O.cpu().numpy().astype(Qa.dtype)
 
 
 def check_accuracy(output, reference, config_str="", max_abs_tol=1e-2, max_rel_tol=0.5, mean_rel_tol=0.05):

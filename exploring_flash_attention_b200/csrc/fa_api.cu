@@ -18,6 +18,7 @@
 #include "../../include/fa_b200.h"
 #include "fa_combine_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_naive_sm100.cuh"
 #include "fa_tiled_d_pair_sm100.cuh"
 #include "fa_tiled_d_sm100.cuh"
 
@@ -437,6 +438,27 @@ struct HostStaging {
   }
 } g_stage[kMaxDevices];
 
+template <typename T>
+int naive_attention_impl(const T* Q, const T* K, const T* V, T* O, int n_heads, int Lq, int Lk, int d, T* scores,
+                         size_t ws_bytes, cudaStream_t s) {
+  const size_t per_head = size_t(Lq) * Lk * sizeof(T);
+  const int chunk = int(std::min<size_t>(size_t(n_heads), std::min<size_t>(ws_bytes / per_head, 65535)));
+  if (chunk < 1) return fail(FA_ERR_WORKSPACE, "workspace must hold the [Lq x Lk] scores of at least one head: " + std::to_string(per_head) + " bytes");
+  const T alpha = T(1) / std::sqrt(T(d));
+  for (int h0 = 0; h0 < n_heads; h0 += chunk) {
+    const int nh = std::min(chunk, n_heads - h0);
+    const T *q = Q + size_t(h0) * Lq * d, *k = K + size_t(h0) * Lk * d, *v = V + size_t(h0) * Lk * d;
+    T* o = O + size_t(h0) * Lq * d;
+    fa::naive_gemm_kernel<T, true><<<dim3((Lk + 63) / 64, (Lq + 63) / 64, nh), 256, 0, s>>>(
+        q, k, scores, Lq, Lk, d, alpha, (long long)Lq * d, (long long)Lk * d, (long long)Lq * Lk);
+    fa::naive_softmax_rows_kernel<T><<<dim3(unsigned(size_t(nh) * Lq)), 256, 0, s>>>(scores, Lk);
+    fa::naive_gemm_kernel<T, false><<<dim3((d + 63) / 64, (Lq + 63) / 64, nh), 256, 0, s>>>(
+        scores, v, o, Lq, d, Lk, T(1), (long long)Lq * Lk, (long long)Lk * d, (long long)Lq * d);
+    FA_CUDA_TRY(cudaGetLastError());
+  }
+  return FA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -627,6 +649,26 @@ int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, i
   rc = fa_v2_splitkv_forward(Q, K, V, o_accum, lse_accum, B, H, L, d, kv_per_split, dtype, stream);
   if (rc != FA_OK) return rc;
   return fa_v2_combine(o_accum, lse_accum, O, B, H, L, d, ns, dtype, stream);
+}
+
+// ---- independent evaluation (drop-in for the reference's oracle naive_attention, common/reference.py:7-21) ----
+size_t fa_naive_attention_workspace_bytes(int n_heads, int Lq, int Lk, int dtype) {
+  if (n_heads <= 0 || Lq <= 0 || Lk <= 0 || (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_F64)) return 0;
+  return size_t(n_heads) * Lq * Lk * (dtype == FA_DTYPE_F64 ? 8 : 4);
+}
+
+int fa_naive_attention(const void* Q, const void* K, const void* V, void* O, int n_heads, int Lq, int Lk, int d,
+                       int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_heads <= 0 || Lq <= 0 || Lk <= 0 || d <= 0) return fail(FA_ERR_SHAPE, "n_heads, Lq, Lk, d must be positive");
+  if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_F64) return fail(FA_ERR_DTYPE, "naive attention computes in FA_DTYPE_F32 or FA_DTYPE_F64");
+  if (!Q || !K || !V || !O || !workspace) return fail(FA_ERR_ALIGN, "Q, K, V, O, workspace must be non-null");
+  if ((long long)n_heads * Lq > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == FA_DTYPE_F64)
+    return naive_attention_impl<double>(static_cast<const double*>(Q), static_cast<const double*>(K), static_cast<const double*>(V),
+                                        static_cast<double*>(O), n_heads, Lq, Lk, d, static_cast<double*>(workspace), workspace_bytes, s);
+  return naive_attention_impl<float>(static_cast<const float*>(Q), static_cast<const float*>(K), static_cast<const float*>(V),
+                                     static_cast<float*>(O), n_heads, Lq, Lk, d, static_cast<float*>(workspace), workspace_bytes, s);
 }
 
 void fa_release_host_staging(void) {

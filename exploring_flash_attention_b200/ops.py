@@ -273,6 +273,32 @@ def flash_attention_v2(Q, K, V, kv_per_split: int, O=None, workspace=None, sync:
     return O
 
 
+def naive_attention_reference(Q, K, V, max_workspace_bytes: int = 1 << 30):
+    """The package's independent evaluation (fa_naive_attention): materialised scores, CUDA-core fp32 / fp64 math.
+    Q [...,Lq,d], K, V [...,Lk,d] float32 or float64 CUDA tensors (any d) -> O like Q."""
+    if not (Q.is_cuda and K.is_cuda and V.is_cuda):
+        raise RuntimeError("flash-attention B200 path needs CUDA tensors: there is no CPU fallback")
+    if Q.dtype not in (torch.float32, torch.float64) or not (Q.dtype == K.dtype == V.dtype):
+        raise _lib.FlashAttentionError(-2, "naive_attention_reference computes in float32 or float64")
+    if Q.dim() < 2 or K.shape != V.shape or Q.shape[:-2] != K.shape[:-2] or Q.shape[-1] != K.shape[-1]:
+        raise _lib.FlashAttentionError(-1, "Q must be [...,Lq,d] and K, V [...,Lk,d]")
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    Lq, d = Q.shape[-2:]
+    Lk = K.shape[-2]
+    n_heads = Q.numel() // (Lq * d)
+    dt = _lib.FA_DTYPE_F64 if Q.dtype == torch.float64 else _lib.FA_DTYPE_F32
+    lib = _lib.load()
+    with torch.cuda.device(Q.device):
+        one = lib.fa_naive_attention_workspace_bytes(1, Lq, Lk, dt)
+        heads_at_once = max(1, min(n_heads, max_workspace_bytes // one))
+        ws = torch.empty(one * heads_at_once, dtype=torch.uint8, device=Q.device)
+        O = torch.empty_like(Q)
+        _lib.check(lib.fa_naive_attention(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), n_heads, Lq, Lk, d, dt,
+                                          ws.data_ptr(), ws.numel(), _stream()))
+        torch.cuda.current_stream().synchronize()
+    return O
+
+
 def flash_attention_host(Qh, Kh, Vh, Oh=None, variant: int = 0, kv_per_split: int = 0):
     """Host-buffer path (H2D x3 + kernel + D2H inside the library), like the reference drivers do around their
     launchers (flash_attention_v1/CUDA/driver.cu:184-247). Tensors are CPU tensors, ideally pinned."""

@@ -29,6 +29,8 @@ extern "C" {
 #define FA_DTYPE_BF16 1 /* bf16 storage, fp32 accumulation */
 #define FA_DTYPE_F16 2  /* fp16 storage, fp32 accumulation (the reference's DATA_TYPE=__half) */
 
+#define FA_DTYPE_F64 3  /* fa_naive_attention only: fp64 storage and math (the reference's float64 oracle runs) */
+
 /* status codes */
 #define FA_OK 0
 #define FA_ERR_SHAPE (-1)         /* non-positive B/H/L/d, bad tile hints */
@@ -120,6 +122,17 @@ int fa_v2_combine(const float* Oaccum, const float* LSEaccum, void* O, int B, in
 /* split-KV + combine with a caller-owned workspace of at least fa_v2_workspace_bytes() bytes */
 int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int kv_per_split,
                   int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- independent evaluation ---------------------------------------------------------------
+ * Replaces  naive_attention(Q, K, V)  common/reference.py:7-21 — the reference's own ORACLE, which its scripts compare
+ * every kernel with.  It therefore shares nothing with the kernels above: the [Lq x Lk] score matrix is materialised
+ * in `workspace` (scores = Q K^T / sqrt(d); row softmax; O = probs V, exactly reference.py:16-21), on the CUDA cores
+ * in full fp32 (FA_DTYPE_F32) or fp64 (FA_DTYPE_F64) — no tensor cores, no tf32, no online softmax.  Any d, any Lq, Lk.
+ * Q [n_heads][Lq][d]; K, V [n_heads][Lk][d]; O like Q.  Heads are processed in groups of as many score matrices as the
+ * workspace holds (at least one: fa_naive_attention_workspace_bytes(1, Lq, Lk, dtype)). */
+size_t fa_naive_attention_workspace_bytes(int n_heads, int Lq, int Lk, int dtype);
+int fa_naive_attention(const void* Q, const void* K, const void* V, void* O, int n_heads, int Lq, int Lk, int d,
+                       int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer convenience (what the reference drivers do around their launchers:
  * cudaMalloc + cudaMemcpy H2D x3 + launch + cudaMemcpy D2H, flash_attention_v1/CUDA/driver.cu:184-247).

@@ -110,3 +110,35 @@ def test_head_range_partitions_everything():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         head_range(8, 2, 2)
+
+
+def test_cpp_consumer_compiles_and_links_against_the_header():
+    """tests/drivers/driver_v1.cu includes include/fa_b200.h from C++ and links -lfa_b200 (run on the GPU by
+    tests/test_parity_round2_gpu.py); here: it builds, and its only repo dependency is the library."""
+    import subprocess
+    from exploring_flash_attention_b200 import _build
+    exe = _build.build_consumer()
+    assert exe.exists()
+    needed = subprocess.run(["readelf", "-d", str(exe)], capture_output=True, text=True).stdout
+    assert "libfa_b200.so" in needed
+
+
+def test_host_entry_point_validates_before_touching_the_device():
+    import torch
+    from exploring_flash_attention_b200 import _lib, ops
+    lib = _lib.load()
+    buf = np.zeros(1024, dtype=np.float32)
+    p = buf.ctypes.data
+    assert lib.fa_forward_host(7, p, p, p, p, 1, 1, 8, 32, 0, 0) == -1           # bad variant: before any cudaMalloc
+    assert lib.fa_forward_host(2, p, p, p, p, 1, 1, 8, 32, 0, 0) == -1           # V2 needs kv_per_split
+    assert lib.fa_forward_host(0, p, p, None, p, 1, 1, 8, 32, 0, 0) == -3
+    assert lib.fa_naive_attention_workspace_bytes(2, 100, 50, 0) == 2 * 100 * 50 * 4
+    assert lib.fa_naive_attention_workspace_bytes(2, 100, 50, 3) == 2 * 100 * 50 * 8
+    assert lib.fa_naive_attention_workspace_bytes(2, 100, 50, 1) == 0             # bf16 is not a naive-attention type
+    assert lib.fa_naive_attention(p, p, p, p, 1, 8, 8, 4, 1, p, 1 << 20, None) == -2
+    q = torch.zeros((1, 2, 8, 32))
+    for bad in (torch.zeros((1, 2, 4, 32)), torch.zeros((1, 2, 8, 32), dtype=torch.float16), torch.zeros((1, 2, 32, 8)).transpose(2, 3)):
+        with pytest.raises(_lib.FlashAttentionError):
+            ops.flash_attention_host(q, bad, q)
+        with pytest.raises(_lib.FlashAttentionError):
+            ops.flash_attention_host(q, q, q, bad)

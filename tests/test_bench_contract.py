@@ -21,6 +21,18 @@ def test_reference_arm_json_line():
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["value"] > 0 and "workload" in j["config"]
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert j["config"] == bench.bench_config("c1")            # the same object the GPU arm prints
+
+
+def test_reference_arm_honours_steps_and_warmup():
+    env = dict(os.environ, FA_BENCH_CPU_HEADS="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "2",
+                        "--workload", "c1"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["steps"] == 4 and j["warmup"] == 2
 
 
 def test_non_rank0_reference_arm_is_silent():

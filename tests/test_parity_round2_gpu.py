@@ -214,3 +214,74 @@ def test_full_c4_tensor_sampled_rows(ops):
     V.fill_(1.0)
     O = ops.flash_attention_v1(Q, K, V, sync=True)
     assert (O.float() - 1).abs().max().item() <= 4e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the package's independent evaluation (drop-in for common/reference.py naive_attention) and the C++ consumer
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,Lq,Lk,d,dtype,tol", [
+    (3, 200, 200, 64, torch.float32, 2e-6), (2, 130, 333, 48, torch.float32, 2e-6), (5, 64, 1000, 20, torch.float64, 1e-13),
+    (1, 1, 1, 1, torch.float64, 1e-15), (2, 257, 257, 128, torch.float64, 1e-13),
+])
+def test_independent_naive_attention_matches_oracle(ops, n, Lq, Lk, d, dtype, tol):
+    g = torch.Generator().manual_seed(31)
+    Q = torch.randn((n, Lq, d), generator=g, dtype=torch.float64).to(dtype).cuda()
+    K, V = (torch.randn((n, Lk, d), generator=g, dtype=torch.float64).to(dtype).cuda() for _ in range(2))
+    O = ops.naive_attention_reference(Q, K, V)
+    O_small_ws = ops.naive_attention_reference(Q, K, V, max_workspace_bytes=1)      # one head's scores at a time
+    assert torch.equal(O, O_small_ws)
+    for h in range(n):
+        ref, _ = reference.naive_attention_ex_f64(Q[h].cpu().numpy(), K[h].cpu().numpy(), V[h].cpu().numpy())
+        assert np.abs(O[h].double().cpu().numpy() - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+def test_dropin_naive_attention_is_not_the_kernel_under_test(ops):
+    """common.reference.naive_attention (the name the reference scripts compare everything with) agrees with the float64
+    oracle far more tightly than the tensor-core kernels can, for any head dim, and in the caller's dtype."""
+    from exploring_flash_attention_b200.common.reference import check_accuracy, naive_attention
+    from exploring_flash_attention_b200.flash_attention_v1 import flash_attention_tiled
+    rng = np.random.default_rng(0)
+    for L, d, dt, tol in ((256, 128, np.float64, 1e-12), (100, 24, np.float64, 1e-12), (300, 64, np.float32, 2e-6), (128, 32, np.float16, 1e-3)):
+        Q, K, V = (rng.standard_normal((L, d)).astype(dt) for _ in range(3))
+        out = naive_attention(Q, K, V)
+        assert out.dtype == dt and out.shape == (L, d)
+        ref = reference.naive_attention_f64(Q, K, V)
+        assert np.abs(out.astype(np.float64) - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    # the reference scripts' own check (numpy_gpu_like_opt2.py __main__): tiled kernel vs naive_attention, float64 buffers
+    L, d = 64, 32
+    Q, K, V = (rng.standard_normal((L, d)) for _ in range(3))
+    O = np.zeros(L * d)
+    flash_attention_tiled(Q.flatten(), K.flatten(), V.flatten(), O, L, d, Bq=8, Bk=8)
+    naive = naive_attention(Q, K, V)
+    diff = np.abs(O.reshape(L, d) - naive).max()
+    assert 0 < diff <= 4e-3          # tf32 products vs fp64: close, and visibly NOT the same computation
+    check_accuracy(O.reshape(L, d), naive, "drop-in V1 vs drop-in oracle")
+
+
+def test_cpp_consumer_runs_and_passes():
+    """The compiled C++ driver (tests/drivers/driver_v1.cu) on the reference V1 driver's own config."""
+    import subprocess
+    from exploring_flash_attention_b200 import _build
+    exe = _build.build_consumer()
+    res = subprocess.run([str(exe), "3"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    assert "Test PASSED" in res.stdout
+
+
+def test_host_staging_on_a_second_device_in_the_same_process(ops):
+    """fa_forward_host caches one staging set PER DEVICE: after a call on cuda:0 a call on cuda:1 must not reuse
+    cuda:0's buffers, streams or events."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = torch.Generator().manual_seed(5)
+    Qh, Kh, Vh = ((torch.rand((1, 4, 512, 128), generator=g) * 2 - 1).bfloat16().pin_memory() for _ in range(3))
+    with torch.cuda.device(0):
+        O0 = ops.flash_attention_host(Qh, Kh, Vh, variant=0).clone()
+    with torch.cuda.device(1):
+        O1 = ops.flash_attention_host(Qh, Kh, Vh, variant=0).clone()
+        O1v2 = ops.flash_attention_host(Qh, Kh, Vh, variant=2, kv_per_split=128).clone()
+    with torch.cuda.device(0):
+        O0b = ops.flash_attention_host(Qh, Kh, Vh, variant=0).clone()
+    assert torch.equal(O0, O1) and torch.equal(O0, O0b)
+    assert (O1v2.float() - O0.float()).abs().max().item() <= 2e-3
+    assert max_err(O0.cuda(), oracle_out(Qh, Kh, Vh)) <= 2e-3

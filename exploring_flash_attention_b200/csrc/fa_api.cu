@@ -19,6 +19,7 @@
 #include "fa_combine_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_naive_sm100.cuh"
+#include "fa_splitkv_sm100.cuh"
 #include "fa_tiled_d_pair_sm100.cuh"
 #include "fa_tiled_d_sm100.cuh"
 
@@ -263,6 +264,69 @@ int dispatch_fwd(const void* Q, const void* K, const void* V, void* O, int BH, i
                   std::to_string(d) + " dtype=" + std::to_string(dtype));
 }
 
+// K3a': split-KV partials when every split is a single KV tile (kv_per_split <= 128), fa_splitkv_sm100.cuh.
+template <int D, int DT, int BN>
+int launch_splitkv_tile(const void* Q, const void* K, const void* V, int BH, int L, int kv_per_split, int n_splits,
+                        float* o_accum, float* lse_accum, cudaStream_t stream) {
+  using T = fa::SplitTileTraits<D, DT, BN>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((long long)n_splits * BH > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (split, head) partial slabs");
+  if ((rc = make_map(&tmQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tmK, K, DT, D, L, BH, BN)) != FA_OK) return rc;
+  if ((rc = make_map(&tmV, V, DT, D, L, BH, BN, /*mn_major_operand=*/true)) != FA_OK) return rc;
+  // the fp32 partials as a [n_splits*BH][L][D] tensor, stored 32 columns (one 128-byte row) x 128 rows at a time
+  if ((rc = make_map(&tmO, o_accum, FA_DTYPE_F32, D, L, n_splits * BH, 128)) != FA_OK) return rc;
+  fa::SplitTileParams p{};
+  p.L = L;
+  p.BH = BH;
+  p.kv_per_split = kv_per_split;
+  p.n_splits = n_splits;
+  p.n_qtiles = (L + 127) / 128;
+  p.n_units = (long long)BH * p.n_qtiles * n_splits;
+  p.scale = 1.0f / std::sqrt(float(D));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse_accum = lse_accum;
+  auto kern = fa::fa_splitkv_tile_kernel<D, DT, BN>;
+  static SmemAttrOnce smem_attr;
+  if ((rc = smem_attr.ensure(kern, T::SMEM_BYTES)) != FA_OK) return rc;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(FA_ERR_CUDA, "cannot query the SM count of the current device");
+  const int grid = p.n_units < sms ? int(p.n_units) : sms;
+  kern<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+int dispatch_splitkv_tile(const void* Q, const void* K, const void* V, int BH, int L, int d, int dtype, int kv_per_split,
+                          int n_splits, float* o_accum, float* lse_accum, cudaStream_t s) {
+#define FA_CASE(DD, DTT)                                                                                              \
+  if (d == DD && dtype == DTT) {                                                                                      \
+    if (kv_per_split <= 64)                                                                                           \
+      return launch_splitkv_tile<DD, DTT, 64>(Q, K, V, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s);         \
+    return launch_splitkv_tile<DD, DTT, 128>(Q, K, V, BH, L, kv_per_split, n_splits, o_accum, lse_accum, s);          \
+  }
+  FA_CASE(128, fa::DT_BF16)
+  FA_CASE(64, fa::DT_BF16)
+  FA_CASE(32, fa::DT_BF16)
+  FA_CASE(128, fa::DT_F16)
+  FA_CASE(64, fa::DT_F16)
+  FA_CASE(32, fa::DT_F16)
+  FA_CASE(32, fa::DT_F32)
+  FA_CASE(64, fa::DT_F32)
+#undef FA_CASE
+  return fail(FA_ERR_UNSUPPORTED_D, "split-KV tile kernel: unsupported d / dtype");
+}
+
+// FA_B200_SPLITKV_TILE=0 keeps short splits on the fused-tile kernel's SPLIT mode (A/B measurements).  Read once.
+bool splitkv_tile_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("FA_B200_SPLITKV_TILE");
+    return !(e && e[0] == '0' && e[1] == '\0');
+  }();
+  return on;
+}
+
 // Optional arguments of the slab tiled-d kernel beyond the reference's dense (Q,K,V,O): key ranges (V2 splits / partials),
 // causal masking, the log-sum-exp output.
 struct TiledDExtra {
@@ -385,6 +449,27 @@ int dispatch_tiled_d(const void* Q, const void* K, const void* V, void* O, int B
 // Does the fused-tile kernel (K1) serve this (d, dtype)?  Otherwise the row is 512-1024 bytes and the slab kernel does.
 bool fused_tile_serves(int d, int dtype) { return d <= 128 && !(dtype == FA_DTYPE_F32 && d > 64); }
 
+// The combine is launched with programmatic stream serialization: it may be scheduled while the kernel before it in the
+// stream (normally the split-KV kernel, which calls griddepcontrol.launch_dependents) is draining, and waits in
+// griddepcontrol.wait until that kernel's partials are complete — the ~3 us launch gap between the two short kernels of
+// a V2 call disappears.  After any other kernel the attribute only means "start after it has finished", as usual.
+template <typename Kern>
+int launch_pdl(Kern kern, unsigned blocks, unsigned threads, cudaStream_t s, const float* o_accum, const float* lse_accum,
+               void* O, long long rows, int n_splits) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, o_accum, lse_accum, O, rows, n_splits));
+  return FA_OK;
+}
+
 template <int D, int DT>
 int launch_combine(const float* o_accum, const float* lse_accum, void* O, long long rows, int n_splits,
                    cudaStream_t s) {
@@ -393,14 +478,11 @@ int launch_combine(const float* o_accum, const float* lse_accum, void* O, long l
   if (n_splits <= fa::kCombineMaxSplitsFast) {
     constexpr int RPB = (fa::kCombineThreads / G) * ((NV >= 2) ? 1 : 2);
     const long long blocks = (rows + RPB - 1) / RPB;
-    fa::fa_combine_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
-  } else {
-    constexpr int RPB = fa::kCombineThreads / G;
-    const long long blocks = (rows + RPB - 1) / RPB;
-    fa::fa_combine_generic_kernel<D, DT><<<(unsigned)blocks, fa::kCombineThreads, 0, s>>>(o_accum, lse_accum, O, rows, n_splits);
+    return launch_pdl(fa::fa_combine_kernel<D, DT>, (unsigned)blocks, fa::kCombineThreads, s, o_accum, lse_accum, O, rows, n_splits);
   }
-  FA_CUDA_TRY(cudaGetLastError());
-  return FA_OK;
+  constexpr int RPB = fa::kCombineThreads / G;
+  const long long blocks = (rows + RPB - 1) / RPB;
+  return launch_pdl(fa::fa_combine_generic_kernel<D, DT>, (unsigned)blocks, fa::kCombineThreads, s, o_accum, lse_accum, O, rows, n_splits);
 }
 
 // Cached device staging for the host-buffer entry point: ONE set per device (buffers, streams and events belong to the
@@ -606,6 +688,10 @@ int fa_v2_splitkv_forward(const void* Q, const void* K, const void* V, float* Oa
     tx.lse_accum = LSEaccum;
     return dispatch_tiled_d_slab(Q, K, V, nullptr, B * H, L, d, dtype, static_cast<cudaStream_t>(stream), tx);
   }
+  // every split a single KV tile (the reference's own C3 geometry: 64 keys per split): the dedicated kernel
+  if (kv_per_split <= 128 && splitkv_tile_enabled())
+    return dispatch_splitkv_tile(Q, K, V, B * H, L, d, dtype, kv_per_split, ns, Oaccum, LSEaccum,
+                                 static_cast<cudaStream_t>(stream));
   return dispatch_fwd<true>(Q, K, V, nullptr, B * H, L, d, dtype, kv_per_split, ns, Oaccum, LSEaccum,
                             static_cast<cudaStream_t>(stream));
 }

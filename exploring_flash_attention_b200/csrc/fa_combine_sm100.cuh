@@ -84,6 +84,7 @@ fa_combine_kernel(const float* __restrict__ o_accum, const float* __restrict__ l
     r[t] = live[t] ? row : rows - 1;  // dead groups shadow the last row so whole warps stay converged for the shuffles
   }
 
+  pdl_wait();   // launched with programmatic stream serialization: the split-KV kernel's partials are complete from here on
   // ---- issue: LSE words first (they come back first), then the first batch of Oaccum vectors
   float e[RPT][KK];
 #pragma unroll
@@ -184,6 +185,7 @@ fa_combine_generic_kernel(const float* __restrict__ o_accum, const float* __rest
   const size_t split_stride = size_t(rows) * D;
   const float* src = o_accum + size_t(r) * D + gl * 4;
 
+  pdl_wait();   // see fa_combine_kernel
   // ---- LSE over splits: lanes of the group take splits gl, gl+G, ... ; shuffle-reduce max and sum.
   float my_max = -CUDART_INF_F;
   for (int k = gl; k < n_splits; k += G) my_max = fmaxf(my_max, __ldg(lse_accum + size_t(k) * rows + r));

@@ -252,6 +252,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (SPLIT) pdl_launch_dependents();   // the combine kernel behind a split-KV launch (see launch_combine)
 
   // Register re-split (launch gives every thread 168): the data-movement warpgroup keeps 72, each softmax thread gets
   // 216 (2*128*216 + 128*72 = 384*168 exactly: an inc that cannot be met from the launch allocation blocks forever).  setmaxnreg sits at the top of each role branch (no control-flow merge after it) so ptxas allocates each

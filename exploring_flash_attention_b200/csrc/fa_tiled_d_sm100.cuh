@@ -120,6 +120,7 @@ fa_tiled_d_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.o_accum != nullptr) pdl_launch_dependents();   // the combine kernel behind a split-KV launch (see launch_combine)
 
   if (warp == 4) {
     // ===================================== TMA producer =====================================

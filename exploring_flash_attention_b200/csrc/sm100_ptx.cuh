@@ -39,6 +39,13 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while the kernel before it in the stream is still running; pdl_wait() blocks until that kernel has completed and its
+// writes are visible (a no-op without the attribute).  pdl_launch_dependents() lets the dependent grid be scheduled as
+// soon as every CTA of this grid has called it (or exited), hiding its launch latency under this grid's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

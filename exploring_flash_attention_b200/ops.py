@@ -56,8 +56,8 @@ def _on_device_of(fn):
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
-        if t is None:
-            return fn(*args, **kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)          # already current: skip the (several us) device-guard round trip
         with torch.cuda.device(t.device):
             return fn(*args, **kwargs)
     return wrapper

@@ -14,7 +14,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = Path(os.environ["FA_B200_LIB"]) if os.environ.get("FA_B200_LIB") else CSRC / "libfa_b200.so"
 SOURCES = ["fa_api.cu"]
 HEADERS = ["sm100_ptx.cuh", "fa_fwd_sm100.cuh", "fa_tiled_d_sm100.cuh", "fa_tiled_d_pair_sm100.cuh", "fa_combine_sm100.cuh",
-           "fa_naive_sm100.cuh", "fa_splitkv_sm100.cuh",
+           "fa_naive_sm100.cuh", "fa_bwd_sm100.cuh", "fa_splitkv_sm100.cuh",
            "../../include/fa_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -30,6 +30,8 @@ SYMBOLS = {
     "fa_v2_splitkv_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "fa_v2_combine": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "fa_v2_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "fa_v1_backward_workspace_bytes": (c_size_t, [c_int] * 3),
+    "fa_v1_backward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [ctypes.c_uint, c_void_p, c_size_t, c_void_p]),
     "fa_naive_attention_workspace_bytes": (c_size_t, [c_int] * 4),
     "fa_naive_attention": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "fa_forward_host": (c_int, [c_int] + [c_void_p] * 4 + [c_int] * 6),

@@ -17,6 +17,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_combine_sm100.cuh"
+#include "fa_bwd_sm100.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_naive_sm100.cuh"
 #include "fa_splitkv_sm100.cuh"
@@ -325,6 +326,50 @@ bool splitkv_tile_enabled() {
     return !(e && e[0] == '0' && e[1] == '\0');
   }();
   return on;
+}
+
+// K4: backward (fa_bwd_sm100.cuh): prep (Delta, LSE in log2 units) + dK/dV pass + dQ pass.
+template <int D, int DT>
+int launch_backward(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE, void* dQ,
+                    void* dK, void* dV, int BH, int L, int causal, float* ws, cudaStream_t stream) {
+  using T = fa::BwdTraits<D, DT>;
+  const int n_tiles = (L + 127) / 128;
+  const int Lp = n_tiles * 128;
+  if ((long long)BH * n_tiles > 0x7fffffffLL) return fail(FA_ERR_SHAPE, "too many (head, tile) blocks");
+  float* lse2 = ws;
+  float* delta = ws + size_t(BH) * Lp;
+  const long long prep_rows = (long long)BH * Lp;
+  fa::fa_bwd_prep_kernel<D, DT><<<unsigned((prep_rows + 7) / 8), 256, 0, stream>>>(O, dO, LSE, lse2, delta, L, Lp, BH);
+  FA_CUDA_TRY(cudaGetLastError());
+  CUtensorMap tQ, tK, tV, tdO, tdQ, tdK, tdV;
+  int rc;
+  if ((rc = make_map(&tQ, Q, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tK, K, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tV, V, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tdO, dO, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tdQ, dQ, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tdK, dK, DT, D, L, BH, 128)) != FA_OK) return rc;
+  if ((rc = make_map(&tdV, dV, DT, D, L, BH, 128)) != FA_OK) return rc;
+  fa::BwdParams p{};
+  p.L = L;
+  p.Lp = Lp;
+  p.BH = BH;
+  p.causal = causal;
+  p.scale = 1.0f / std::sqrt(float(D));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse2 = lse2;
+  p.delta = delta;
+  auto k_dkv = fa::fa_bwd_kernel<D, DT, true>;
+  auto k_dq = fa::fa_bwd_kernel<D, DT, false>;
+  static SmemAttrOnce attr_dkv, attr_dq;
+  if ((rc = attr_dkv.ensure(k_dkv, T::SMEM_BYTES)) != FA_OK) return rc;
+  if ((rc = attr_dq.ensure(k_dq, T::SMEM_BYTES)) != FA_OK) return rc;
+  const unsigned grid = unsigned(BH * n_tiles);
+  k_dkv<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tK, tV, tQ, tdO, tdK, tdV, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  k_dq<<<grid, T::THREADS, T::SMEM_BYTES, stream>>>(tQ, tdO, tK, tV, tdQ, tdQ, p);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
 }
 
 // Optional arguments of the slab tiled-d kernel beyond the reference's dense (Q,K,V,O): key ranges (V2 splits / partials),
@@ -735,6 +780,39 @@ int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, i
   rc = fa_v2_splitkv_forward(Q, K, V, o_accum, lse_accum, B, H, L, d, kv_per_split, dtype, stream);
   if (rc != FA_OK) return rc;
   return fa_v2_combine(o_accum, lse_accum, O, B, H, L, d, ns, dtype, stream);
+}
+
+size_t fa_v1_backward_workspace_bytes(int B, int H, int L) {
+  if (B <= 0 || H <= 0 || L <= 0) return 0;
+  return size_t(2) * size_t(B) * H * (size_t((L + 127) / 128) * 128) * sizeof(float);
+}
+
+int fa_v1_backward(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE, void* dQ,
+                   void* dK, void* dV, int B, int H, int L, int d, int dtype, unsigned flags, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  int rc = check_common(Q, K, V, dQ, B, H, L, d, dtype);
+  if (rc != FA_OK) return rc;
+  const void* more[4] = {O, dO, dK, dV};
+  for (const void* ptr : more)
+    if (ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+      return fail(FA_ERR_ALIGN, "O, dO, dK, dV must be non-null and 16-byte aligned");
+  if (LSE == nullptr) return fail(FA_ERR_ALIGN, "LSE must be non-null (fa_v1_forward_ex produces it)");
+  if (flags & ~unsigned(FA_FLAG_CAUSAL)) return fail(FA_ERR_SHAPE, "unknown flag bits");
+  const size_t need = fa_v1_backward_workspace_bytes(B, H, L);
+  if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(FA_ERR_WORKSPACE, "workspace must be 256-byte aligned and hold " + std::to_string(need) + " bytes");
+  const int causal = (flags & FA_FLAG_CAUSAL) ? 1 : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+#define FA_CASE(DD, DTT) \
+  if (d == DD && dtype == DTT) return launch_backward<DD, DTT>(Q, K, V, O, dO, LSE, dQ, dK, dV, B * H, L, causal, ws, s);
+  FA_CASE(128, fa::DT_BF16)
+  FA_CASE(64, fa::DT_BF16)
+  FA_CASE(128, fa::DT_F16)
+  FA_CASE(64, fa::DT_F16)
+#undef FA_CASE
+  return fail(FA_ERR_UNSUPPORTED_D, "backward serves d in {64,128} for bf16/fp16; got d=" + std::to_string(d) +
+                                        " dtype=" + std::to_string(dtype));
 }
 
 // ---- independent evaluation (drop-in for the reference's oracle naive_attention, common/reference.py:7-21) ----

@@ -1,0 +1,337 @@
+// fa_bwd_sm100.cuh — K4: flash-attention BACKWARD for sm_100a (the reference has no backward pass —
+// its README lists only "Flash Attention V3" as future work, README.md:80-84 — so this widens the path rather than
+// replacing a reference kernel; its float64 gradient oracle, pinned to finite differences, lives with the test infrastructure).
+//
+// Given Q, K, V, O = softmax(Q K^T / sqrt d) V, the row log-sum-exp LSE (fa_v1_forward_ex) and dO:
+//     P  = exp(Q K^T / sqrt d - LSE)            (recomputed tile by tile, never stored: the flash-attention recurrence
+//     dV = P^T dO                                 of flash_attention_v1/numpy_gpu_like_opt2.py:161-195 run backwards)
+//     dP = dO V^T,   Delta_i = sum_c dO_ic O_ic,   dS = P o (dP - Delta)
+//     dQ = dS K / sqrt d,   dK = dS^T Q / sqrt d
+// Three kernels:
+//   fa_bwd_prep_kernel          Delta and LSE*log2(e) into a row-padded fp32 workspace (padding rows: LSE = +inf, so P = 0).
+//   fa_bwd_kernel<.., DKV=true>  one CTA per (head, 128-key tile), loops over query tiles, accumulates dK and dV in TMEM.
+//   fa_bwd_kernel<.., DKV=false> one CTA per (head, 128-query tile), loops over key tiles, accumulates dQ in TMEM.
+// (Two passes recompute S and dP — 7 GEMMs instead of 5 — but need no atomics and no fp32 dQ scratch, are deterministic,
+// and are the same code: only which operand pair is resident and which is streamed differs.)
+//
+// One iteration (R = resident pair, S = streamed pair; DKV: R = (K,V), S = (Q_j,dO_j); DQ: R = (Q,dO), S = (K_j,V_j)):
+//     T1 = R0 S0^T   (DKV: S^T = K Q^T  [keys x queries];  DQ: S  = Q K^T  [queries x keys])      SS MMA, both K-major
+//     T2 = R1 S1^T   (DKV: dP^T = V dO^T;                  DQ: dP = dO V^T)
+//     softmax warps (thread <-> TMEM lane): P = exp2(T1*c - lse2), dS = P*(T2 - Delta); lse2/Delta are indexed by COLUMN
+//       in DKV mode (read from the padded workspace, warp-uniform addresses) and by ROW in DQ mode (two scalars);
+//       P and dS are written back over T1 / T2 as packed 16-bit A operands.
+//     DKV: dV += P dO_j   (A = P from TMEM, B = dO_j as MN-major)     and    dK += dS Q_j
+//     DQ :                                                                    dQ += dS K_j
+//   TMEM: T1 [0,128) T2 [128,256) ACC0 [256,256+D) (dK | dQ) ACC1 [256+D,256+2D) (dV).
+//   warps 0-3 softmax + epilogue, warp 4 TMA producer (streamed pair double-buffered), warp 5 tcgen05.mma issuer.
+// 16-bit dtypes, d in {64, 128}.  Causal: tiles strictly above the diagonal are skipped, the diagonal tile is masked.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "fa_fwd_sm100.cuh"
+
+namespace fa {
+
+struct BwdParams {
+  int L;            // rows per head (queries == keys)
+  int Lp;           // padded row count of the workspace rows: ceil(L / 128) * 128
+  int BH;
+  int causal;
+  float scale;      // 1/sqrt(d)
+  float scale_log2; // log2(e)/sqrt(d)
+  const float* lse2;   // [BH][Lp] LSE * log2(e); +inf on padding rows
+  const float* delta;  // [BH][Lp] rowsum(dO o O); 0 on padding rows
+};
+
+// Delta_i = sum_c dO_ic * O_ic and LSE in log2 units, one warp per row.
+template <int D, int DT>
+__global__ void __launch_bounds__(256)
+fa_bwd_prep_kernel(const void* __restrict__ O, const void* __restrict__ dO, const float* __restrict__ lse,
+                   float* __restrict__ lse2, float* __restrict__ delta, int L, int Lp, int BH) {
+  const long long row_p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // row index in the padded [BH][Lp] space
+  if (row_p >= (long long)BH * Lp) return;
+  const int lane = threadIdx.x & 31;
+  const int bh = int(row_p / Lp), r = int(row_p % Lp);
+  if (r >= L) {
+    if (lane == 0) {
+      lse2[row_p] = CUDART_INF_F;
+      delta[row_p] = 0.f;
+    }
+    return;
+  }
+  const size_t base = (size_t(bh) * L + r) * D;
+  float acc = 0.f;
+  for (int c = lane * 2; c < D; c += 64) {
+    float o0, o1, g0, g1;
+    if constexpr (DT == DT_BF16) {
+      const uint32_t ow = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(O) + base + c);
+      const uint32_t gw = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(dO) + base + c);
+      o0 = __uint_as_float(ow << 16);
+      o1 = __uint_as_float(ow & 0xffff0000u);
+      g0 = __uint_as_float(gw << 16);
+      g1 = __uint_as_float(gw & 0xffff0000u);
+    } else {
+      const __half2 oh = *reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(O) + base + c);
+      const __half2 gh = *reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(dO) + base + c);
+      o0 = __low2float(oh);
+      o1 = __high2float(oh);
+      g0 = __low2float(gh);
+      g1 = __high2float(gh);
+    }
+    acc = fmaf(o0, g0, fmaf(o1, g1, acc));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    delta[row_p] = acc;
+    lse2[row_p] = lse[size_t(bh) * L + r] * 1.4426950408889634f;
+  }
+}
+
+template <int D, int DT>
+struct BwdTraits {
+  using F = FwdTraits<D, DT>;
+  static_assert(DT != DT_F32 && (D == 64 || D == 128), "backward: 16-bit dtypes, d = 64 or 128");
+  static constexpr int TILE_BYTES = F::TILE_BYTES;               // one [128 x D] operand tile
+  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1;
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES /*resident pair*/ + 4 * TILE_BYTES /*2 stages x streamed pair*/ +
+                                    NUM_BARS * 8 + 16;
+  static constexpr int THREADS = 192;
+  static constexpr int TM_T1 = 0, TM_T2 = 128, TM_ACC0 = 256, TM_ACC1 = 256 + D;
+};
+
+template <int D, int DT, bool DKV>
+__global__ void __launch_bounds__(192, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
+              const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
+              const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1, const BwdParams p) {
+  using T = BwdTraits<D, DT>;
+  using F = typename T::F;
+  constexpr int TILE_BYTES = T::TILE_BYTES, NBLK = F::NBLK, BLK_BYTES = F::BLK_BYTES, BLK_ELEMS = F::BLK_ELEMS, UK = F::UK;
+  constexpr uint32_t KIND = F::KIND;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR = smem;                          // [2] resident tiles R0, R1
+  uint8_t* sS = smem + 2 * TILE_BYTES;         // [2 stages][2] streamed tiles S0, S1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + 4 * TILE_BYTES);
+  uint64_t* r_full = bars;            // [1] TMA -> MMA: resident pair landed
+  uint64_t* s_full = r_full + 1;      // [2] TMA -> MMA: streamed pair of this stage landed
+  uint64_t* s_empty = s_full + 2;     // [2] MMA (commit) -> TMA: every MMA reading this stage retired
+  uint64_t* t_full = s_empty + 2;     // [1] MMA -> softmax: T1, T2 of this iteration ready
+  uint64_t* pds_full = t_full + 1;    // [1] softmax (128 arrivals) -> MMA: P and dS written over T1 / T2
+  uint64_t* acc_done = pds_full + 1;  // [1] MMA -> epilogue: every accumulating MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.L + 127) / 128;
+  const int tile = blockIdx.x % n_tiles;       // DKV: key tile of this CTA; DQ: query tile
+  const int bh = blockIdx.x / n_tiles;
+  const int row0 = tile * 128;
+  // streamed tiles this CTA visits: causal DKV -> query tiles tile..n-1; causal DQ -> key tiles 0..tile
+  const int j_begin = (p.causal && DKV) ? tile : 0;
+  const int j_end = (p.causal && !DKV) ? tile + 1 : n_tiles;
+  const int n_iter = j_end - j_begin;
+
+  if (warp == 5 && lane == 0) {
+    mbar_init(r_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmR0);
+      tma_prefetch_desc(&tmR1);
+      tma_prefetch_desc(&tmS0);
+      tma_prefetch_desc(&tmS1);
+      tma_prefetch_desc(&tmOut0);
+      if (DKV) tma_prefetch_desc(&tmOut1);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================================== TMA producer =====================================
+    if (elect_one_sync()) {
+      auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int row) {
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) tma_load_3d(dst + b * BLK_BYTES, map, bar, b * BLK_ELEMS, row, bh);
+      };
+      mbar_arrive_expect_tx(r_full, 2 * TILE_BYTES);
+      load_tile(sR, &tmR0, r_full, row0);
+      load_tile(sR + TILE_BYTES, &tmR1, r_full, row0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        if (it >= 2) mbar_wait(&s_empty[st], ((it >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&s_full[st], 2 * TILE_BYTES);
+        load_tile(sS + (2 * st) * TILE_BYTES, &tmS0, &s_full[st], (j_begin + it) * 128);
+        load_tile(sS + (2 * st + 1) * TILE_BYTES, &tmS1, &s_full[st], (j_begin + it) * 128);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================== MMA issuer ========================================
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_t = make_idesc(F::FMT, 128, 128, 0, 0);    // T = A B^T, both K-major
+      constexpr uint32_t idesc_acc = make_idesc(F::FMT, 128, D, 0, 1);    // acc += A(TMEM) B, B MN-major
+      constexpr uint64_t hiK = make_smem_desc_hi(16, 8 * F::SWB, F::SWZ);
+      constexpr uint64_t hiMN = make_smem_desc_hi(BLK_BYTES, 8 * F::SWB, F::SWZ);
+      const uint32_t sR_addr = smem_u32(sR), sS_addr = smem_u32(sS);
+      auto mma_t = [&](uint32_t t_col, uint32_t a_base, uint32_t b_base) {   // T[t_col..+128) = A B^T over d
+#pragma unroll
+        for (int k = 0; k < D / UK; ++k) {
+          const uint32_t off = (k / F::KPR) * BLK_BYTES + (k % F::KPR) * 32;
+          umma_ss<KIND>(tmem_base + t_col, make_smem_desc(a_base + off, hiK), make_smem_desc(b_base + off, hiK), idesc_t,
+                        k > 0 ? 1u : 0u);
+        }
+      };
+      auto mma_acc = [&](uint32_t acc_col, uint32_t a_col, uint32_t b_base, uint32_t acc) {   // acc += A(TMEM) B over 128 rows
+#pragma unroll
+        for (int kk = 0; kk < 128 / UK; ++kk)
+          umma_ts<KIND>(tmem_base + acc_col, tmem_base + a_col + kk * (UK * F::ES / 4),
+                        make_smem_desc(b_base + kk * UK * F::SWB, hiMN), idesc_acc, (acc | (kk > 0)) ? 1u : 0u);
+      };
+      mbar_wait(r_full, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t s0 = sS_addr + (2 * st) * TILE_BYTES, s1 = s0 + TILE_BYTES;
+        mbar_wait(&s_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        // T1/T2 were last read (as P/dS) by the accumulating MMAs of the previous iteration: same thread, in-order pipe
+        mma_t(T::TM_T1, sR_addr, s0);
+        mma_t(T::TM_T2, sR_addr + TILE_BYTES, s1);
+        tc_commit(t_full);
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        if (DKV) mma_acc(T::TM_ACC1, T::TM_T1, s1, it > 0 ? 1u : 0u);   // dV += P dO_j
+        mma_acc(T::TM_ACC0, T::TM_T2, s0, it > 0 ? 1u : 0u);            // dK += dS Q_j   |   dQ += dS K_j
+        tc_commit(&s_empty[st]);
+      }
+      tc_commit(acc_done);
+    }
+  } else {
+    // ===================================== softmax + epilogue warps ===========================
+    const int row = warp * 32 + lane;                                 // TMEM lane = local row of the resident tile
+    const uint32_t t_lane = tmem_base + (uint32_t(warp * 32) << 16);
+    const size_t ws_head = size_t(bh) * p.Lp;
+    float my_lse2 = 0.f, my_delta = 0.f;
+    if (!DKV) {
+      my_lse2 = p.lse2[ws_head + row0 + row];
+      my_delta = p.delta[ws_head + row0 + row];
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int j = j_begin + it;
+      const bool diag = p.causal && (j == tile);
+      const float* lse_col = p.lse2 + ws_head + j * 128;     // DKV: per-column (query) statistics of this streamed tile
+      const float* delta_col = p.delta + ws_head + j * 128;
+      mbar_wait(t_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {   // 32 columns at a time
+        uint32_t t1[32], t2[32];
+        tmem_ld32(t_lane + T::TM_T1 + c * 32, t1);
+        tmem_ld32(t_lane + T::TM_T2 + c * 32, t2);
+        tc_wait_ld();
+        uint32_t pp[16], ds[16];
+#pragma unroll
+        for (int x = 0; x < 32; x += 4) {
+          float4 l4, d4;
+          if (DKV) {
+            l4 = __ldg(reinterpret_cast<const float4*>(lse_col + c * 32 + x));
+            d4 = __ldg(reinterpret_cast<const float4*>(delta_col + c * 32 + x));
+          } else {
+            l4 = make_float4(my_lse2, my_lse2, my_lse2, my_lse2);
+            d4 = make_float4(my_delta, my_delta, my_delta, my_delta);
+          }
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pv[4], sv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c * 32 + x + e;
+            float pe = ex2_approx(fmaf(__uint_as_float(t1[x + e]), p.scale_log2, -lv[e]));
+            // causal diagonal tile: DKV lanes are keys, columns queries (keep query >= key); DQ the other way round
+            if (diag && (DKV ? (col < row) : (col > row))) pe = 0.f;
+            pv[e] = pe;
+            sv[e] = pe * (__uint_as_float(t2[x + e]) - dv[e]);
+          }
+          pp[x / 2] = (DT == DT_BF16) ? pack_bf16x2(pv[0], pv[1]) : pack_f16x2(pv[0], pv[1]);
+          pp[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(pv[2], pv[3]) : pack_f16x2(pv[2], pv[3]);
+          ds[x / 2] = (DT == DT_BF16) ? pack_bf16x2(sv[0], sv[1]) : pack_f16x2(sv[0], sv[1]);
+          ds[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(sv[2], sv[3]) : pack_f16x2(sv[2], sv[3]);
+        }
+        // packed columns [16c, 16c+16) overwrite T columns that chunks <= c/2 have already read
+        if (DKV) tmem_st16(t_lane + T::TM_T1 + c * 16, pp);
+        tmem_st16(t_lane + T::TM_T2 + c * 16, ds);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+
+    // ------------------------------- epilogue: accumulators -> 16-bit -> smem -> TMA store ----
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const uint32_t stg_addr = smem_u32(sS);          // the streamed stages are dead: one [128 x 128 B] block per output block
+    const bool storer = (warp == 0) && (lane == 0);
+    constexpr int N_OUT = DKV ? 2 : 1;
+#pragma unroll
+    for (int which = 0; which < N_OUT; ++which) {
+      const float mul = (which == 0) ? p.scale : 1.0f;   // dK, dQ carry the 1/sqrt(d) of the scores; dV does not
+      const uint32_t tA = t_lane + (which == 0 ? T::TM_ACC0 : T::TM_ACC1);
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        const uint32_t blk = stg_addr + (which * NBLK + b) * BLK_BYTES;
+        constexpr int CPB = BLK_ELEMS / 32;   // 32-column TMEM loads per 128-byte block: 2 (16-bit)
+#pragma unroll
+        for (int h = 0; h < CPB; ++h) {
+          uint32_t o[32];
+          tmem_ld32(tA + b * BLK_ELEMS + h * 32, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {   // 8 elements = 16 bytes per chunk
+            auto pk2 = [&](int e) {
+              const float a0 = __uint_as_float(o[e]) * mul, a1 = __uint_as_float(o[e + 1]) * mul;
+              return (DT == DT_BF16) ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
+            };
+            uint4 v;
+            v.x = pk2(8 * u + 0);
+            v.y = pk2(8 * u + 2);
+            v.z = pk2(8 * u + 4);
+            v.w = pk2(8 * u + 6);
+            const int chunk = h * 4 + u;   // 16-byte chunk index inside the 128-byte block row
+            st_shared_v4(blk + row * 128 + ((chunk ^ (row & 7)) << 4), v);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (storer) {
+#pragma unroll
+      for (int which = 0; which < N_OUT; ++which)
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b)
+          tma_store_3d(which == 0 ? &tmOut0 : &tmOut1, sS + (which * NBLK + b) * BLK_BYTES, b * BLK_ELEMS, row0, bh);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace fa

@@ -273,6 +273,36 @@ def flash_attention_v2(Q, K, V, kv_per_split: int, O=None, workspace=None, sync:
     return O
 
 
+@_on_device_of
+def flash_attention_backward(Q, K, V, O, dO, LSE, causal: bool = False, workspace=None, sync: bool = False):
+    """Gradients (dQ, dK, dV) of O = softmax(Q K^T / sqrt(d)) V for [B,H,L,d] bf16 / fp16 tensors, d in {64, 128}.
+    O and LSE come from flash_attention_v1_ex(..., causal=causal, return_lse=True).  `workspace`: optional uint8 CUDA
+    tensor of backward_workspace_bytes(B, H, L) bytes, reused across calls."""
+    Q, K, V = _prep(Q, K, V)
+    B, H, L, d = Q.shape
+    O = _check_buffer(O, Q.shape, Q.dtype, Q.device, "O")
+    dO = _check_buffer(dO.contiguous(), Q.shape, Q.dtype, Q.device, "dO")
+    LSE = _check_buffer(LSE, (B, H, L), torch.float32, Q.device, "LSE")
+    lib = _lib.load()
+    need = lib.fa_v1_backward_workspace_bytes(B, H, L)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=Q.device)
+    elif (not isinstance(workspace, torch.Tensor) or workspace.device != Q.device or workspace.dtype != torch.uint8
+          or workspace.numel() < need or not workspace.is_contiguous()):
+        raise _lib.FlashAttentionError(-6, f"workspace must be a contiguous uint8 tensor of at least {need} bytes on {Q.device}")
+    dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+    _lib.check(lib.fa_v1_backward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(), LSE.data_ptr(),
+                                  dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), B, H, L, d, _DTYPES[Q.dtype],
+                                  1 if causal else 0, workspace.data_ptr(), workspace.numel(), _stream()))
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    return dQ, dK, dV
+
+
+def backward_workspace_bytes(B: int, H: int, L: int) -> int:
+    return _lib.load().fa_v1_backward_workspace_bytes(B, H, L)
+
+
 def naive_attention_reference(Q, K, V, max_workspace_bytes: int = 1 << 30):
     """The package's independent evaluation (fa_naive_attention): materialised scores, CUDA-core fp32 / fp64 math.
     Q [...,Lq,d], K, V [...,Lk,d] float32 or float64 CUDA tensors (any d) -> O like Q."""

@@ -123,6 +123,17 @@ int fa_v2_combine(const float* Oaccum, const float* LSEaccum, void* O, int B, in
 int fa_v2_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int L, int d, int kv_per_split,
                   int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- backward (the reference has no backward pass: README.md:80-84 lists only "Flash Attention V3"
+ * as future work).  Gradients of O = softmax(Q K^T / sqrt(d)) V with respect to Q, K, V given dO:
+ *   Q, K, V, O, dO  [B,H,L,d] (O and LSE as produced by fa_v1_forward_ex with the same flags);  LSE [B*H*L] fp32;
+ *   dQ, dK, dV      [B,H,L,d] outputs in the same dtype;  flags: FA_FLAG_CAUSAL.
+ * The probabilities are recomputed tile by tile from Q, K and LSE (never stored).  workspace: caller-owned,
+ * fa_v1_backward_workspace_bytes() bytes, 256-byte aligned (row statistics).  bf16 / fp16, d in {64, 128}. */
+size_t fa_v1_backward_workspace_bytes(int B, int H, int L);
+int fa_v1_backward(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE, void* dQ,
+                   void* dK, void* dV, int B, int H, int L, int d, int dtype, unsigned flags, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- independent evaluation ---------------------------------------------------------------
  * Replaces  naive_attention(Q, K, V)  common/reference.py:7-21 — the reference's own ORACLE, which its scripts compare
  * every kernel with.  It therefore shares nothing with the kernels above: the [Lq x Lk] score matrix is materialised

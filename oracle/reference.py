@@ -80,3 +80,24 @@ def naive_attention_batched_f64(Q, K, V, heads=None, rows=None):
         p /= p.sum(axis=1, keepdims=True)
         out.append(p @ v)
     return np.stack(out)
+
+
+def attention_backward_f64(Q, K, V, dO, causal=False):
+    """Analytic gradient of naive_attention (common/reference.py:15-21) for one head, float64:
+    S = Q K^T / sqrt(d), P = softmax(S) (row-wise; causal: keys above the diagonal excluded), O = P V;
+      dV = P^T dO;  dP = dO V^T;  dS = P o (dP - rowsum(dP o P));  dQ = dS K / sqrt(d);  dK = dS^T Q / sqrt(d).
+    (rowsum(dP o P) = rowsum(dO o O): the Delta of the flash-attention backward.)  The reference has no backward pass
+    (README.md:80-84); tests/test_oracle.py pins this against central finite differences of naive_attention_ex_f64.
+    [L,d] x4 -> (dQ, dK, dV)."""
+    Q, K, V, dO = (np.asarray(x, dtype=np.float64) for x in (Q, K, V, dO))
+    L, d = Q.shape
+    scale = 1.0 / np.sqrt(d)
+    s = (Q @ K.T) * scale
+    if causal:
+        s = np.where(np.tril(np.ones((L, K.shape[0]), dtype=bool)), s, -np.inf)
+    p = np.exp(s - s.max(axis=1, keepdims=True))
+    p /= p.sum(axis=1, keepdims=True)
+    dV = p.T @ dO
+    dP = dO @ V.T
+    dS = p * (dP - (dP * p).sum(axis=1, keepdims=True))
+    return (dS @ K) * scale, (dS.T @ Q) * scale, dV

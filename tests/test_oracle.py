@@ -137,3 +137,28 @@ def test_extended_oracle_reduces_to_reference_and_masks():
     np.testing.assert_allclose(Oc[0], V[0], atol=1e-15)                       # row 0 sees key 0 only
     np.testing.assert_allclose(Oc[-1], O[-1], atol=1e-14)                     # last row sees everything
     np.testing.assert_allclose(lsec[3], np.log(np.exp(s[3, :4]).sum()), atol=1e-12)
+
+
+def test_backward_oracle_matches_finite_differences():
+    """attention_backward_f64 (the backward's oracle; the reference has no backward) against central differences of the
+    forward oracle, dense and causal, on a loss sum(O * W)."""
+    from oracle import reference
+    rng = np.random.default_rng(5)
+    L, d = 12, 8
+    Q, K, V, W = (rng.standard_normal((L, d)) for _ in range(4))
+    for causal in (False, True):
+        dQ, dK, dV = reference.attention_backward_f64(Q, K, V, W, causal=causal)
+        loss = lambda q, k, v: float((reference.naive_attention_ex_f64(q, k, v, causal=causal)[0] * W).sum())
+        eps = 1e-6
+        for X, dX, idx in ((Q, dQ, 0), (K, dK, 1), (V, dV, 2)):
+            num = np.zeros_like(X)
+            for i in range(L):
+                for c in range(d):
+                    Xp, Xm = X.copy(), X.copy()
+                    Xp[i, c] += eps
+                    Xm[i, c] -= eps
+                    args_p = [Q, K, V]
+                    args_m = [Q, K, V]
+                    args_p[idx], args_m[idx] = Xp, Xm
+                    num[i, c] = (loss(*args_p) - loss(*args_m)) / (2 * eps)
+            assert np.abs(num - dX).max() <= 1e-7, (causal, idx, np.abs(num - dX).max())

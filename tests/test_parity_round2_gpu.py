@@ -285,3 +285,51 @@ def test_host_staging_on_a_second_device_in_the_same_process(ops):
     assert torch.equal(O0, O1) and torch.equal(O0, O0b)
     assert (O1v2.float() - O0.float()).abs().max().item() <= 2e-3
     assert max_err(O0.cuda(), oracle_out(Qh, Kh, Vh)) <= 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward: dQ, dK, dV against the float64 analytic gradient (itself pinned to finite differences)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,L,d,dtype", [
+    (1, 2, 256, 128, torch.bfloat16), (2, 2, 384, 64, torch.bfloat16), (1, 2, 512, 128, torch.float16),
+    (1, 3, 333, 128, torch.bfloat16), (1, 2, 100, 64, torch.float16), (1, 1, 129, 128, torch.bfloat16),
+    (1, 1, 1, 64, torch.bfloat16), (1, 2, 1000, 64, torch.bfloat16),
+])
+def test_backward_matches_analytic_gradient(ops, B, H, L, d, dtype):
+    """Parity bar for the backward: max-abs error <= 5e-3 of the gradient's own magnitude (max |grad|), per tensor."""
+    Q, K, V = uniform_qkv(B, H, L, d, dtype)
+    g = torch.Generator().manual_seed(99)
+    dO = ((torch.rand((B, H, L, d), generator=g) * 2 - 1)).to(dtype).cuda()
+    f = lambda x: x.float().cpu().numpy().reshape(B * H, L, d).astype(np.float64)
+    for causal in (False, True):
+        O, lse = ops.flash_attention_v1_ex(Q, K, V, causal=causal, return_lse=True, sync=True)
+        dQ, dK, dV = ops.flash_attention_backward(Q, K, V, O, dO, lse, causal=causal, sync=True)
+        for t in (dQ, dK, dV):
+            assert not torch.isnan(t).any() and not torch.isinf(t).any()
+        for h in range(B * H):
+            rQ, rK, rV = reference.attention_backward_f64(f(Q)[h], f(K)[h], f(V)[h], f(dO)[h], causal=causal)
+            for name, got, ref in (("dQ", f(dQ)[h], rQ), ("dK", f(dK)[h], rK), ("dV", f(dV)[h], rV)):
+                err = np.abs(got - ref).max()
+                assert err <= 5e-3 * max(np.abs(ref).max(), 1e-3), (name, causal, h, err, np.abs(ref).max())
+
+
+def test_backward_c2_shape_sampled_heads(ops):
+    """BASELINE.json configs[1] shape (B32 H8 L1024 d128 bf16): sampled heads against the float64 gradient."""
+    B, H, L, d = 32, 8, 1024, 128
+    Q, K, V = uniform_qkv(B, H, L, d, torch.bfloat16)
+    dO = (torch.rand((B, H, L, d), generator=torch.Generator().manual_seed(7)) * 2 - 1).bfloat16().cuda()
+    O, lse = ops.flash_attention_v1_ex(Q, K, V, return_lse=True, sync=True)
+    ws = torch.empty(ops.backward_workspace_bytes(B, H, L), dtype=torch.uint8, device="cuda")
+    dQ, dK, dV = ops.flash_attention_backward(Q, K, V, O, dO, lse, workspace=ws, sync=True)
+    f = lambda x, h: x.reshape(B * H, L, d)[h].float().cpu().numpy().astype(np.float64)
+    for h in (0, 131, B * H - 1):
+        rQ, rK, rV = reference.attention_backward_f64(f(Q, h), f(K, h), f(V, h), f(dO, h))
+        for got, ref in ((f(dQ, h), rQ), (f(dK, h), rK), (f(dV, h), rV)):
+            assert np.abs(got - ref).max() <= 5e-3 * np.abs(ref).max()
+    from exploring_flash_attention_b200 import FlashAttentionError
+    with pytest.raises(FlashAttentionError):
+        ops.flash_attention_backward(Q, K, V, O, dO, lse, workspace=ws[:100])
+    q32 = torch.zeros((1, 1, 128, 32), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(FlashAttentionError) as ei:
+        ops.flash_attention_backward(q32, q32, q32, q32, q32, torch.zeros((1, 1, 128), device="cuda"))
+    assert ei.value.code == -4

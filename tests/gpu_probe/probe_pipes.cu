@@ -63,6 +63,22 @@ __device__ __forceinline__ void body(float2 (&a)[ILP], float c, float d) {
       a[k].x = __uint_as_float(r);
     } else if constexpr (OP == 17) {  // LOP3/PRMT unpack-like: shl
       a[k].x = __uint_as_float(__float_as_uint(a[k].x) << 16);
+    } else if constexpr (OP == 18) {  // FHADD: fp32 += fp16 (mixed-precision add)
+      uint16_t hh = (uint16_t)__float_as_uint(a[k].y);
+      asm volatile("add.rn.f32.f16 %0, %1, %0;" : "+f"(a[k].x) : "h"(hh));
+    } else if constexpr (OP == 19) {  // HADD2.F16
+      uint32_t r = __float_as_uint(a[k].x), cc = __float_as_uint(c);
+      asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(r) : "r"(cc));
+      a[k].x = __uint_as_float(r);
+    } else if constexpr (OP == 20) {  // candidate fp16 softmax pair: FFMA2 + F2FP.F16 + MUFU.f16x2 + HADD2
+      float2 v = __ffma2_rn(a[k], make_float2(c, c), make_float2(d, d));
+      uint32_t r;
+      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r));
+      uint32_t acc = __float_as_uint(a[(k + 1) % ILP].y);
+      asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(acc) : "r"(r));
+      a[(k + 1) % ILP].y = __uint_as_float(acc);
+      a[k].x = __uint_as_float(r);
     }
   }
 }
@@ -121,6 +137,9 @@ int main() {
   run<9>("IMAD", 1);
   run<16>("HFMA2.BF16", 1);
   run<17>("SHL", 1);
+  run<18>("FHADD f32+=f16", 1);
+  run<19>("HADD2.F16", 1);
+  run<20>("mix FFMA2+F2FP+MUFUf16x2+HADD2 (per pair)", 1);
   run<14>("mix FFMA2+2MUFU+FADD2 (per pair)", 1);
   run<15>("mix 2FFMA+2MUFU+2FADD (per pair)", 1);
   return 0;

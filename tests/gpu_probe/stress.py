@@ -16,12 +16,18 @@ n = 0
 worst = {}
 while time.time() < t_end:
     dtype = rng.choice([torch.bfloat16, torch.float16, torch.float32])
-    d = rng.choice([32, 64] if dtype == torch.float32 else [32, 64, 128, 128, 256, 512])
+    d = rng.choice([32, 64, 128, 256] if dtype == torch.float32 else [32, 64, 128, 128, 256, 512])
     L = rng.choice([1, 7, 64, 127, 128, 129, 255, 256, 257, 300, 511, 640, 1000, 1024, 1500, 2048, 3000])
-    if d >= 256:
+    big_rows = d >= 256 or (dtype == torch.float32 and d >= 128)     # rows of 512-1024 bytes: the tiled-d kernels
+    if big_rows:
         L = min(L, 1024)
     BH = rng.choice([1, 2, 3, 5, 37, 149, 300]) if L <= 300 else rng.choice([1, 2, 3, 5, 19])
-    variant = rng.choice(["v1", "v1", "v2", "varlen", "causal", "parts"]) if d <= 128 else rng.choice(["td", "tdp"])
+    if big_rows:
+        variant = rng.choice(["td", "tdp", "v2", "varlen", "causal", "parts"] if dtype != torch.float32 else
+                             ["td", "v2", "varlen", "causal", "parts"])
+    else:
+        variant = rng.choice(["v1", "v1", "v2", "v2", "varlen", "causal", "parts"] +
+                             (["bwd", "bwd"] if dtype != torch.float32 and d in (64, 128) else []))
     g = torch.Generator().manual_seed(n)
     Q, K, V = ((torch.rand((1, BH, L, d), generator=g) * 2 - 1).to(dtype).cuda() for _ in range(3))
     mask = None          # [BH, Lq, Lk] bool of attended keys, when the variant masks
@@ -50,6 +56,28 @@ while time.time() < t_end:
         O = ops.flash_attention_v2_combine(o_parts, lse_parts, dtype, (1, BH, L, d))
         torch.cuda.synchronize()
         tag = f"parts/{len(bounds) - 1}"
+    elif variant == "bwd":
+        causal = rng.random() < 0.5
+        dO = ((torch.rand((1, BH, L, d), generator=g) * 2 - 1).to(dtype)).cuda()
+        O, lse = ops.flash_attention_v1_ex(Q, K, V, causal=causal, return_lse=True, sync=True)
+        grads = ops.flash_attention_backward(Q, K, V, O, dO, lse, causal=causal, sync=True)
+        nh = min(BH, 3)
+        idx = torch.tensor(sorted(rng.sample(range(BH), nh)), device="cuda")
+        q, k, v = (x[0, idx].double().requires_grad_(True) for x in (Q, K, V))
+        sc = q @ k.transpose(-1, -2) / d ** 0.5
+        if causal:
+            sc = sc.masked_fill(~torch.ones((L, L), dtype=torch.bool, device="cuda").tril(), float("-inf"))
+        (torch.softmax(sc, -1) @ v * dO[0, idx].double()).sum().backward()
+        for name, got, ref in zip(("dQ", "dK", "dV"), grads, (q.grad, k.grad, v.grad)):
+            err = (got[0, idx].double() - ref).abs().max().item()
+            # P and dS enter the tensor core as 16-bit operands: 2^-9 relative rounding each for bf16 (the pytest cases sit
+            # at 3-4e-3 of max|grad|, random shapes reach 5.1e-3), 2^-12 for fp16
+            rel_tol = 1e-2 if dtype == torch.bfloat16 else 5e-3
+            if not (err <= rel_tol * max(ref.abs().max().item(), 1e-3)) or torch.isnan(got).any():
+                print(f"FAIL case {n}: bwd {name} causal={causal} dtype={dtype} BH={BH} L={L} d={d} err={err} max|ref|={ref.abs().max().item()}", flush=True)
+                sys.exit(1)
+        n += 1
+        continue
     elif variant == "v1":
         O = ops.flash_attention_v1(Q, K, V, sync=True)
         tag = "v1"
@@ -60,7 +88,7 @@ while time.time() < t_end:
         O = ops.flash_attention_v1_tiled_d_pair(Q, K, V, sync=True)
         tag = "tdp"
     else:
-        kvs = rng.choice([8, 64, 100, 128, 256, 1000])
+        kvs = rng.choice([8, 16, 64, 64, 100, 128, 128, 256, 1000])
         O = ops.flash_attention_v2(Q, K, V, kvs, sync=True)
         tag = f"v2/{kvs}"
     nh = min(BH, 4)

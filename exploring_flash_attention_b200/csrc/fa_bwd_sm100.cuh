@@ -34,6 +34,10 @@
 
 #include "fa_fwd_sm100.cuh"
 
+#ifndef FA_BWD_WAIT
+#define FA_BWD_WAIT mbar_wait   // polling or mbar_wait_sleep (suspend-time hint), A/B-tested per kernel
+#endif
+
 namespace fa {
 
 struct BwdParams {
@@ -180,7 +184,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       load_tile(sR + TILE_BYTES, &tmR1, r_full, row0);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
-        if (it >= 2) mbar_wait(&s_empty[st], ((it >> 1) - 1) & 1);
+        if (it >= 2) FA_BWD_WAIT(&s_empty[st], ((it >> 1) - 1) & 1);
         mbar_arrive_expect_tx(&s_full[st], 2 * TILE_BYTES);
         load_tile(sS + (2 * st) * TILE_BYTES, &tmS0, &s_full[st], (j_begin + it) * 128);
         load_tile(sS + (2 * st + 1) * TILE_BYTES, &tmS1, &s_full[st], (j_begin + it) * 128);
@@ -216,14 +220,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
         const int st = it & 1;
         const uint32_t s0 = sS_addr + (2 * st) * TILE_BYTES, s1 = s0 + TILE_BYTES;
         if (h == 0) {
-          mbar_wait(&s_full[st], (it >> 1) & 1);
+          FA_BWD_WAIT(&s_full[st], (it >> 1) & 1);
           tc_fence_after();
         }
         mma_t(T::TM_T1, sR_addr, s0, h);
         mma_t(T::TM_T2, sR_addr + TILE_BYTES, s1, h);
         tc_commit(&t_full[h]);
       };
-      mbar_wait(r_full, 0);
+      FA_BWD_WAIT(r_full, 0);
       // issue order: T0(0) T1(0) | acc0(0) T0(1) | acc1(0) T1(1) | acc0(1) T0(2) | ...   (T_h(it+1) overwrites the columns
       // acc_h(it) has just read: same thread, in-order pipe)
       if (n_iter > 0) {
@@ -235,7 +239,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
         const uint32_t s0 = sS_addr + (2 * st) * TILE_BYTES, s1 = s0 + TILE_BYTES;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&pds_full[h], it & 1);
+          FA_BWD_WAIT(&pds_full[h], it & 1);
           tc_fence_after();
           if (DKV) mma_acc(T::TM_ACC1, T::TM_T1, s1, (it > 0 || h > 0) ? 1u : 0u, h);   // dV += P dO_j
           mma_acc(T::TM_ACC0, T::TM_T2, s0, (it > 0 || h > 0) ? 1u : 0u, h);            // dK += dS Q_j   |   dQ += dS K_j
@@ -262,7 +266,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       const float* delta_col = p.delta + ws_head + j * 128;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {   // columns [64h, 64h+64) belong to half h
-      mbar_wait(&t_full[h], it & 1);
+      FA_BWD_WAIT(&t_full[h], it & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {   // 32 columns at a time
@@ -318,7 +322,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
     }
 
     // ------------------------------- epilogue: accumulators -> 16-bit -> smem -> TMA store ----
-    mbar_wait(acc_done, 0);
+    FA_BWD_WAIT(acc_done, 0);
     tc_fence_after();
     const uint32_t stg_addr = smem_u32(sS);          // the streamed stages are dead: one [128 x 128 B] block per output block
     const bool storer = (warp == 0) && (lane == 0);

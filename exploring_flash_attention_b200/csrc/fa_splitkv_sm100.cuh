@@ -32,6 +32,10 @@
 
 #include "fa_fwd_sm100.cuh"
 
+#ifndef FA_SKV_WAIT
+#define FA_SKV_WAIT mbar_wait   // polling or mbar_wait_sleep (suspend-time hint), A/B-tested per kernel
+#endif
+
 namespace fa {
 
 template <int D, int DT, int BN_>
@@ -182,7 +186,7 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int split = uc.split, bh = uc.bh, q_row0 = uc.qt * T::BM;
           if (n == 0 || split == 0) {
             const int qi = nq & 1;
-            if (nq >= 2) mbar_wait(&q_empty[qi], ((nq >> 1) - 1) & 1);
+            if (nq >= 2) FA_SKV_WAIT(&q_empty[qi], ((nq >> 1) - 1) & 1);
             mbar_arrive_expect_tx(&q_full[qi], T::Q_BYTES);
 #pragma unroll
             for (int b = 0; b < NBLK; ++b)
@@ -190,7 +194,7 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             ++nq;
           }
           const int stage = n % NR;
-          if (n >= NR) mbar_wait(&k_empty[stage], ((n / NR) - 1) & 1);
+          if (n >= NR) FA_SKV_WAIT(&k_empty[stage], ((n / NR) - 1) & 1);
           mbar_arrive_expect_tx(&k_full[stage], T::KV_BYTES);
 #pragma unroll
           for (int b = 0; b < NBLK; ++b)
@@ -204,7 +208,7 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         UnitCursor uc(u_begin, p);
         for (int n = 0; n < n_local; ++n, uc.next(p)) {
           const int stage = n % NR;
-          if (n >= NR) mbar_wait(&v_empty[stage], ((n / NR) - 1) & 1);
+          if (n >= NR) FA_SKV_WAIT(&v_empty[stage], ((n / NR) - 1) & 1);
           mbar_arrive_expect_tx(&v_full[stage], T::KV_BYTES);
 #pragma unroll
           for (int b = 0; b < NBLK; ++b)
@@ -227,13 +231,13 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int split = qk_split;
           qk_split = (qk_split + 1 == p.n_splits) ? 0 : qk_split + 1;
           if (n == 0 || split == 0) {
-            mbar_wait(&q_full[nq & 1], (nq >> 1) & 1);
+            FA_SKV_WAIT(&q_full[nq & 1], (nq >> 1) & 1);
             ++nq;
           }
           const int qi = (nq - 1) & 1;
           const int sb = n % NSB;
           const int stage = n % NR;
-          mbar_wait(&k_full[stage], (n / NR) & 1);
+          FA_SKV_WAIT(&k_full[stage], (n / NR) & 1);
           tc_fence_after();
           const uint32_t a_base = sQ_addr + qi * T::Q_BYTES, b_base = sK_addr + stage * T::KV_BYTES;
 #pragma unroll
@@ -255,9 +259,9 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int sb = n % NSB, ks = n / NSB;
           const int ob = n & 1, ko = n >> 1;
           const int stage = n % NR;
-          mbar_wait(&v_full[stage], (n / NR) & 1);
-          if (ko > 0) mbar_wait(&o_free[ob], (ko - 1) & 1);   // O[ob] of unit n-2 has been read out
-          mbar_wait(&p_full[sb], ks & 1);
+          FA_SKV_WAIT(&v_full[stage], (n / NR) & 1);
+          if (ko > 0) FA_SKV_WAIT(&o_free[ob], (ko - 1) & 1);   // O[ob] of unit n-2 has been read out
+          FA_SKV_WAIT(&p_full[sb], ks & 1);
           tc_fence_after();
           const uint32_t b_base = sV_addr + stage * T::KV_BYTES;
 #pragma unroll
@@ -285,7 +289,7 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int valid = min(p.L, kv_begin + p.kv_per_split) - kv_begin;   // 1 .. BN keys of this tile count
       const uint32_t tS = t_lane + T::TM_S + sb * BN;
 
-      mbar_wait(&s_full[sb], ks & 1);
+      FA_SKV_WAIT(&s_full[sb], ks & 1);
       tc_fence_after();
       uint32_t s[NB][32];
 #pragma unroll
@@ -373,7 +377,7 @@ fa_splitkv_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int ob = n & 1, ko = n >> 1;
       const int split = uc.split, bh = uc.bh, q_row0 = uc.qt * T::BM;
       const uint32_t tO = t_lane + T::TM_O + ob * D;
-      mbar_wait(&o_done[ob], ko & 1);
+      FA_SKV_WAIT(&o_done[ob], ko & 1);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < D / 32; c0 += SC / 32, ++chunk_no) {

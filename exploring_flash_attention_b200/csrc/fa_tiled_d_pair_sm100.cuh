@@ -151,7 +151,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       int it = 0;
       auto acquire = [&]() -> int {   // returns the stage; the leader arms its barrier for both CTAs' bytes
         const int stage = it % NS;
-        if (it >= NS) mbar_wait(&empty[stage], ((it / NS) - 1) & 1);
+        if (it >= NS) mbar_wait_sleep(&empty[stage], ((it / NS) - 1) & 1);
         if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
         ++it;
         return stage;
@@ -191,7 +191,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       auto qk = [&](int b) {  // S[b] = Q K^T, accumulated over the d chunks as they land
         for (int s = 0; s < KST; ++s) {
           const int stage = it % NS;
-          mbar_wait(&full[stage], (it / NS) & 1);
+          mbar_wait_sleep(&full[stage], (it / NS) & 1);
           tc_fence_after();
 #pragma unroll
           for (int e = 0; e < 2; ++e)
@@ -209,7 +209,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       auto pv = [&](int b, uint32_t acc) {  // O[:, 128g .. 128g+127] (+)= P[b] V(:, group g)
         for (int g = 0; g < NG; ++g) {
           const int stage = it % NS;
-          mbar_wait(&full[stage], (it / NS) & 1);
+          mbar_wait_sleep(&full[stage], (it / NS) & 1);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk)
@@ -222,7 +222,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         tc_commit_pair(&pv_done[b], 3);
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_sleep(q_full, 0);
       tc_fence_after();
       for (int j = 0; j < NB - 1 && j < n_tiles; ++j) qk(j);
       int b = 0, b_ahead = NB - 1;   // j % NB, (j + NB - 1) % NB
@@ -255,7 +255,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t tS = t_lane + T::TM_S + b * 64;
       // S[b] ready; in-order completion also proves PV(j-NB) retired, i.e. P[b] may be overwritten.
-      mbar_wait(&s_full[b], par);
+      mbar_wait_sleep(&s_full[b], par);
       tc_fence_after();
       uint32_t s[2][32];
       tmem_ld32(tS, s[0]);
@@ -293,7 +293,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (__any_sync(0xffffffffu, need)) {
           // O may only be touched once PV(j-1) has retired.  Its barrier last completed for tile j-1-NB (proved by
           // S(j) being ready) and cannot complete again before this thread signals P(j): the parity is unambiguous.
-          mbar_wait(&pv_done[b_prev], par_prev);
+          mbar_wait_sleep(&pv_done[b_prev], par_prev);
           tc_fence_after();
           const float alpha = need ? ex2_approx((m_used - mx) * p.scale_log2) : 1.0f;
           if (need) m_used = mx;
@@ -370,7 +370,7 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     l_buf[t] = l;
     named_bar_sync(1, 128);
     const float inv_l = 1.0f / (l + l_buf[t ^ 64]);
-    mbar_wait(&pv_done[b_prev], par_prev);   // the last PV (same parity argument as in the rescale branch)
+    mbar_wait_sleep(&pv_done[b_prev], par_prev);   // the last PV (same parity argument as in the rescale branch)
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < NG * 2; ++c) {   // 32 columns at a time; group g = c >> 1 holds d = 128g + 64*half + [0,64)

@@ -548,7 +548,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
               // MUFU does 16 ex2/clk/SM, as many cycles per KV tile as the tensor pipe needs at d=128 and 2-4x more
               // at d<=64, so every FA_POLY_MOD-th element pair is evaluated on the FMA pipes instead.
-              if (FA_POLY_MOD > 0 && ((x >> 1) % (FA_POLY_MOD > 0 ? FA_POLY_MOD : 1)) == FA_POLY_MOD - 1) {
+              // (16-bit d = 64 — P in its own TMEM columns, QK ahead of the softmax — does best with one pair in eight:
+              //  +6.5 % at L = 8192, profiles/r2_poly_ab.txt; every other instantiation with one in FA_POLY_MOD)
+              constexpr int PM = (FA_POLY_MOD == 4 && D == 64 && DT != DT_F32) ? 8 : FA_POLY_MOD;
+              if (PM > 0 && ((x >> 1) % (PM > 0 ? PM : 1)) == PM - 1) {
                 v = exp2_poly2(v);
               } else {
                 v.x = ex2_approx(v.x);

@@ -395,6 +395,16 @@ def ring_checks(torch, dist, ops, rank, world, max_over_ranks, barrier):
             # same rule as tests/test_parity_gpu.py: 2e-3 on averaged rows; early causal rows are O(1) copies of V rows, whose
             # bf16 storage rounding alone is 2^-9 of their magnitude
             tols["causal" if causal else "dense"] = 2e-3 * max(1.0, 2.0 * float(np.abs(ref).max()))
+            # the same rows by head exchange (sharding.alltoall_attention): rank-order row blocks also when causal
+            mine_a = [x[:, :, rank * Ls:(rank + 1) * Ls].cuda().contiguous() for x in (Qf, Kf, Vf)]
+            try:
+                O = sharding.alltoall_attention(*mine_a, causal=causal)
+                torch.cuda.synchronize()
+                err = float(np.abs(O.float().cpu().numpy().reshape(B * H, -1, d) - ref[:, rank * Ls:(rank + 1) * Ls]).max())
+            except Exception as e:  # noqa: BLE001
+                err = float("nan")
+                res[f"error_alltoall_{'causal' if causal else 'dense'}"] = str(e)[:200]
+            errs[f"alltoall_{'causal' if causal else 'dense'}"] = max_over_ranks(err)
         res["max_abs_err"] = errs
         res["tolerance"] = tols
         res["parity_ok"] = all(e <= tols["causal" if k.endswith("causal") else "dense"] for k, e in errs.items())
@@ -431,6 +441,23 @@ def ring_checks(torch, dist, ops, rank, world, max_over_ranks, barrier):
             fl = flops(B, H, L, d) * (0.5 if causal else 1.0)
             timings["causal" if causal else "dense"] = {"ms": round(ms, 3), "tflops": round(fl / (ms * 1e-3) / 1e12, 1)}
         res["c4_sequence_sharded_peer_transport"] = timings
+        a2a = {}
+        for causal in (False, True):
+            for _ in range(2):
+                sharding.alltoall_attention(q, k, v, causal=causal)
+            barrier()
+            n = 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                sharding.alltoall_attention(q, k, v, causal=causal)
+            e1.record()
+            e1.synchronize()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1) / n)
+            fl = flops(B, H, L, d) * (0.5 if causal else 1.0)
+            a2a["causal" if causal else "dense"] = {"ms": round(ms, 3), "tflops": round(fl / (ms * 1e-3) / 1e12, 1)}
+        res["c4_sequence_sharded_alltoall"] = a2a
     except Exception as e:  # noqa: BLE001
         res["ring_c4_error"] = str(e)[:300]
     return res

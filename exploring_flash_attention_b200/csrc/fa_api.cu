@@ -835,6 +835,16 @@ int fa_naive_attention(const void* Q, const void* K, const void* V, void* O, int
                                      static_cast<float*>(O), n_heads, Lq, Lk, d, static_cast<float*>(workspace), workspace_bytes, s);
 }
 
+// Strided block copy on the copy engines (no SMs): `height` rows of `width` bytes, row pitches dpitch / spitch, between any
+// two device pointers the current device can address (its own memory or peer-mapped symmetric memory).  The all-to-all
+// sequence-parallel path moves [heads][rows][d] blocks with it while the persistent attention kernel owns every SM.
+int fa_copy_2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream) {
+  if (!dst || !src || width == 0 || height == 0 || dpitch < width || spitch < width)
+    return fail(FA_ERR_SHAPE, "fa_copy_2d_async: null pointer, empty block or pitch smaller than the row width");
+  FA_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return FA_OK;
+}
+
 void fa_release_host_staging(void) {
   const int dev = current_device();
   if (dev < 0) return;

@@ -486,6 +486,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int my_tiles = c.nt(i);
       const int row_q = c.q_row0 + i * BM + row;   // my query row inside the head
       for (int j = 0; j < my_tiles; ++j, ++nt) {
+        // (Tried: __nanosleep(150..300) here when P aliases S — S_i(j) cannot be ready before PV_i(j-1) + QK_i(j), >= 768
+        //  tensor cycles after this warp published P — so the warp would not poll beside the other tile's warp: +-0.)
         mbar_wait(&s_full[i], nt & 1);
         if (row == 0) FA_TR(i, nt, 0, 0);
         tc_fence_after();

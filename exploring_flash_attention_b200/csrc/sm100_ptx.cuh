@@ -149,6 +149,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 template <uint32_t SUSPEND_NS>
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_t<SUSPEND_NS>(bar, parity)) return;   // already complete: no loop state at all
+  // (A tighter poll loop — eight try_waits back to back in one asm block, two issue slots per failed poll — is SLOWER:
+  //  K1 -6 %, the slab tiled-d kernel -20 % (profiles/r2_poll8_ab.txt): it polls more often, and every poll takes an issue
+  //  slot from the softmax warp sharing the sub-partition.  The loop below is deliberately not minimal.)
   uint32_t polls = 0;
   unsigned long long t0 = 0;
   while (!mbar_try_wait_t<SUSPEND_NS>(bar, parity)) {

@@ -201,3 +201,137 @@ def ring_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None
         if s + 1 < world:
             kv, nxt = nxt, kv
     return combine_fn(o_parts, lse_parts, Q.dtype, (B, H, Ls, d))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sequence-sharded attention by head exchange (all-to-all), the NVSwitch-native alternative to the ring
+# ---------------------------------------------------------------------------------------------------------------------
+_a2a_state: dict = {}
+
+
+def _a2a_buffers(BH, hpr, Ls, L, d, dtype, device, group):
+    """Symmetric (peer-mapped) staging for the local Q, K, V rows ([3,BH,Ls,d]) and for the outputs of the heads this rank
+    computes ([hpr,L,d]); two local [3,hc,L,d] assembly buffers are allocated by the caller per chunk size."""
+    import torch.distributed._symmetric_memory as symm_mem
+    pg = group if group is not None else dist.group.WORLD
+    key = (pg.group_name, BH, Ls, d, dtype, device.index)
+    if key not in _a2a_state:
+        src = symm_mem.empty((3, BH, Ls, d), dtype=dtype, device=device)
+        out = symm_mem.empty((hpr, L, d), dtype=dtype, device=device)
+        h_src = symm_mem.rendezvous(src, pg)
+        h_out = symm_mem.rendezvous(out, pg)
+        streams = tuple(torch.cuda.Stream(device) for _ in range(3))
+        _a2a_state[key] = (src, out, h_src, h_out, streams, {})
+    return _a2a_state[key]
+
+
+def _copy_2d(dst, src, stream):
+    """dst, src: [n, rows, d] tensors whose [rows, d] blocks are dense and whose leading stride may differ (a row window of
+    a taller tensor): one cudaMemcpy2DAsync on `stream` — copy engines, no SMs."""
+    from . import _lib
+    n, rows, d = src.shape
+    es = src.element_size()
+    assert dst.shape == src.shape and dst.stride(-1) == 1 and src.stride(-1) == 1 and dst.stride(-2) == d and src.stride(-2) == d
+    _lib.check(_lib.load().fa_copy_2d_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
+                                            rows * d * es, n, stream.cuda_stream))
+
+
+def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None, causal: bool = False,
+                       transport: str = "auto", chunks: int = 4, attn_fn=None):
+    """Attention over a sequence sharded across the ranks of `group`, by exchanging heads instead of circulating K/V.
+
+    Q, K, V: this rank's [B,H,Ls,d] rows (rank r owns rows [r*Ls, (r+1)*Ls), also when causal); B*H must be a multiple
+    of the world size.  Every rank fetches, for ITS share of the heads, the rows of all ranks (one all-to-all), runs the
+    plain fused-tile kernel over the full sequence for those heads — no partials, no merge, causal balanced for free —
+    and the outputs travel back by the inverse exchange.  On NVSwitch every GPU reaches every peer at full bandwidth,
+    so the exchange costs 2*(N-1)/N of one Q,K,V,O pass over NVLink instead of the ring's N partial passes through HBM
+    (the ring writes and re-reads N fp32 partials: 8x the output bytes on 8 GPUs); the same (b,h) independence that makes
+    head sharding communication-free (flash_attention_v1/CUDA/flash_attention_v1.h:170-172) is what allows it.
+
+    transport "peer" (CUDA default): rows are staged once in symmetric memory; each rank PULLS the blocks it needs with
+      copy-engine 2-D copies (fa_copy_2d_async) on side streams, `chunks` head groups deep, so the pulls of group c+1
+      hide under the attention kernel of group c; outputs are pulled back the same way after one barrier.
+    transport "collective": two dist.all_to_all_single calls (any backend; used by the gloo CPU tests).
+    attn_fn(q, k, v) -> o on [1,h,L,d] tensors defaults to ops.flash_attention_v1_ex(causal=causal).
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if Q.dim() != 4 or Q.shape != K.shape or Q.shape != V.shape:
+        raise ValueError("Q, K, V must be [B,H,Ls,d] shards with identical shapes")
+    B, H, Ls, d = Q.shape
+    BH = B * H
+    if BH % world != 0:
+        raise ValueError("B*H must be a multiple of the world size (heads are exchanged whole)")
+    if transport not in ("auto", "peer", "collective"):
+        raise ValueError("transport must be 'auto', 'peer' or 'collective'")
+    if transport == "auto":
+        transport = "peer" if Q.is_cuda else "collective"
+    if attn_fn is None:
+        from . import ops
+        attn_fn = lambda q, k, v, out=None: ops.flash_attention_v1_ex(q, k, v, out, causal=causal)
+    hpr = BH // world            # heads this rank computes: flat heads [rank*hpr, (rank+1)*hpr)
+    L = Ls * world
+
+    if transport == "collective" or world == 1:
+        def to_heads(x):         # [B,H,Ls,d] -> my heads over the whole sequence [hpr, L, d]
+            send = x.reshape(world, hpr, Ls, d).contiguous()
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send, group=group)          # recv[p] = rank p's rows of my heads
+            return recv.permute(1, 0, 2, 3).reshape(hpr, L, d).contiguous()
+        q, k, v = to_heads(Q), to_heads(K), to_heads(V)
+        o = attn_fn(q[None], k[None], v[None])[0]                    # [hpr, L, d]
+        send = o.reshape(hpr, world, Ls, d).permute(1, 0, 2, 3).contiguous()   # [p] = my heads' rows owned by rank p
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)              # recv[p] = rank p's heads, my rows
+        return recv.reshape(B, H, Ls, d)
+
+    src, out_sym, h_src, h_out, streams, cache = _a2a_buffers(BH, hpr, Ls, L, d, Q.dtype, Q.device, group)
+    main = torch.cuda.current_stream(Q.device)
+    src[0].copy_(Q.reshape(BH, Ls, d))
+    src[1].copy_(K.reshape(BH, Ls, d))
+    src[2].copy_(V.reshape(BH, Ls, d))
+    h_src.barrier(channel=0)     # every rank's rows are staged (and every rank has left the previous call)
+    n_chunks = max(1, min(chunks, hpr))
+    bounds = [hpr * c // n_chunks for c in range(n_chunks + 1)]
+    hc_max = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
+    if "full" not in cache or cache["full"].shape[2] < hc_max:
+        cache["full"] = torch.empty((2, 3, hc_max, L, d), dtype=Q.dtype, device=Q.device)
+    full = cache["full"]
+    peers = [h_src.get_buffer(p, src.shape, src.dtype) for p in range(world)]
+    h0 = rank * hpr
+
+    def pull(c):
+        """Rows of all ranks for head chunk c -> full[c % 2]; Q, K, V on separate copy streams."""
+        hb, he = bounds[c], bounds[c + 1]
+        events = []
+        for t, st in enumerate(streams):
+            st.wait_stream(main)             # the kernel of chunk c-2, last reader of full[c % 2], is already enqueued
+            for s in range(world):
+                p = (rank + s) % world       # start with the local block, then a different peer per rank
+                _copy_2d(full[c % 2, t, :he - hb, p * Ls:(p + 1) * Ls], peers[p][t, h0 + hb:h0 + he], st)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            events.append(ev)
+        return events
+
+    pending = pull(0)
+    for c in range(n_chunks):
+        hb, he = bounds[c], bounds[c + 1]
+        for ev in pending:
+            main.wait_event(ev)
+        if c + 1 < n_chunks:
+            pending = pull(c + 1)            # travels while the kernel of chunk c runs
+        q, k, v = (full[c % 2, t, :he - hb][None] for t in range(3))
+        attn_fn(q, k, v, out_sym[hb:he][None])
+    h_out.barrier(channel=0)     # every rank's outputs are complete
+    O = torch.empty((BH, Ls, d), dtype=Q.dtype, device=Q.device)
+    outs = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype) for p in range(world)]
+    for s in range(world):
+        p = (rank + s) % world
+        st = streams[s % len(streams)]
+        st.wait_stream(main)
+        _copy_2d(O[p * hpr:(p + 1) * hpr], outs[p][:, rank * Ls:(rank + 1) * Ls], st)
+    for st in streams:
+        main.wait_stream(st)
+    h_out.barrier(channel=1)     # nobody restages or overwrites outputs while a peer may still be pulling them
+    return O.reshape(B, H, Ls, d)

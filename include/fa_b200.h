@@ -153,6 +153,11 @@ int fa_forward_host(int variant, const void* Qh, const void* Kh, const void* Vh,
                     int kv_per_split, int dtype);
 void fa_release_host_staging(void);   /* frees the CURRENT device's staging buffers (one cached set per device) */
 
+/* Strided block copy on the copy engines (cudaMemcpy2DAsync, cudaMemcpyDefault): `height` rows of `width` bytes.  Used
+ * by the sequence-parallel all-to-all path (sharding.alltoall_attention) to move [heads][rows][d] blocks between peer-
+ * mapped buffers without taking SMs from the attention kernel. */
+int fa_copy_2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+
 /* Diagnostics: how many TMA tensor maps were served from the per-thread cache / had to be encoded by the driver since
  * the library was loaded (launching on the same buffers step after step must not re-encode; the reference re-derives
  * its launch state on every call, flash_attention_v1.h:280-292).  Either pointer may be NULL. */

@@ -130,3 +130,54 @@ def test_two_gpu_ring_attention(transport, causal):
         ref = reference.naive_attention_batched_f64(Q, K, V)
         tol = 2e-3
     assert np.abs(full.reshape(ref.shape) - ref).max() <= tol
+
+
+def _a2a_worker(rank, world, port, q, transport, causal):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from exploring_flash_attention_b200.sharding import alltoall_attention
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    B, H, L, d = 2, 5, 1024, 128            # 10 heads over 2 ranks, 5 each, in 4 pipelined chunks (2+1+1+1)
+    g = torch.Generator().manual_seed(78)
+    Q, K, V = ((torch.rand((B, H, L, d), generator=g) * 2 - 1).bfloat16() for _ in range(3))
+    Ls = L // world
+    qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous().cuda() for x in (Q, K, V))
+    local = alltoall_attention(qs, ks, vs, transport=transport, causal=causal)
+    assert torch.equal(local, alltoall_attention(qs, ks, vs, transport=transport, causal=causal))   # buffers are reused
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put((out.float().cpu().numpy(), Q.float().numpy(), K.float().numpy(), V.float().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("transport,causal", [("peer", False), ("peer", True), ("collective", False)])
+def test_two_gpu_alltoall_attention(transport, causal):
+    """Sequence-sharded attention by head exchange: copy-engine pulls out of the peers' symmetric memory (or NCCL
+    all-to-all), the plain fused-tile kernel over whole sequences for this rank's heads, outputs pulled back."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import reference
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q, transport, causal)) for r in range(2)]
+    for p in procs:
+        p.start()
+    shards, Q, K, V = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    full = np.concatenate(list(shards), axis=2)            # [B,H,L,d] from the per-rank row blocks
+    B, H, L, d = Q.shape
+    ref = np.stack([reference.naive_attention_ex_f64(Q.reshape(-1, L, d)[h], K.reshape(-1, L, d)[h], V.reshape(-1, L, d)[h],
+                                                     causal=causal)[0] for h in range(B * H)])
+    tol = 2e-3 * (max(1.0, 2 * np.abs(ref).max()) if causal else 1.0)
+    assert np.abs(full.reshape(ref.shape) - ref).max() <= tol

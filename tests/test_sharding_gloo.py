@@ -125,3 +125,55 @@ def test_ring_attention_schedule_over_gloo(causal):
         full = np.concatenate(list(shards), axis=2)
         ref = reference.naive_attention_batched_f64(Q.numpy(), K.numpy(), V.numpy())
     np.testing.assert_allclose(full.reshape(B * H, L, d), ref, atol=1e-5)
+
+
+def _a2a_worker(rank, world, port, B, H, L, d, causal, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from exploring_flash_attention_b200.sharding import alltoall_attention
+    from oracle import reference
+    g = torch.Generator().manual_seed(9)
+    Q, K, V = (torch.rand((B, H, L, d), generator=g) * 2 - 1 for _ in range(3))     # same tensors on every rank
+    Ls = L // world
+    qs, ks, vs = (x[:, :, rank * Ls:(rank + 1) * Ls].contiguous() for x in (Q, K, V))
+    seen = []
+
+    def attn_fn(q_, k_, v_, out=None):           # oracle stand-in for the CUDA kernel: [1,h,L,d] -> [1,h,L,d]
+        seen.append(tuple(q_.shape))
+        o = np.stack([reference.naive_attention_ex_f64(q_[0, i].numpy(), k_[0, i].numpy(), v_[0, i].numpy(), causal=causal)[0]
+                      for i in range(q_.shape[1])])
+        return torch.from_numpy(o).float()[None]
+
+    local = alltoall_attention(qs, ks, vs, causal=causal, attn_fn=attn_fn)
+    assert seen == [(1, B * H // world, L, d)]    # this rank computed its share of the heads over the WHOLE sequence
+    out = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(out, local)
+    if rank == 0:
+        q.put(torch.cat(out, dim=2).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_alltoall_attention_over_gloo(causal):
+    """Sequence sharded over 3 ranks, heads exchanged by all-to-all: every rank sees whole sequences for a third of the
+    heads and the reassembled rows equal unsharded attention."""
+    B, H, L, d, world = 2, 3, 30, 8, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, world, port, B, H, L, d, causal, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, str(ROOT))
+    from oracle import reference
+    g = torch.Generator().manual_seed(9)
+    Q, K, V = (torch.rand((B, H, L, d), generator=g) * 2 - 1 for _ in range(3))
+    ref = np.stack([reference.naive_attention_ex_f64(Q.reshape(-1, L, d)[h].numpy(), K.reshape(-1, L, d)[h].numpy(),
+                                                     V.reshape(-1, L, d)[h].numpy(), causal=causal)[0] for h in range(B * H)])
+    np.testing.assert_allclose(full.reshape(B * H, L, d), ref, atol=1e-5)

@@ -220,7 +220,7 @@ def _a2a_buffers(BH, hpr, Ls, L, d, dtype, device, group):
         out = symm_mem.empty((hpr, L, d), dtype=dtype, device=device)
         h_src = symm_mem.rendezvous(src, pg)
         h_out = symm_mem.rendezvous(out, pg)
-        streams = tuple(torch.cuda.Stream(device) for _ in range(3))
+        streams = tuple(torch.cuda.Stream(device) for _ in range(4))   # Q, K, V pulls + the output pulls
         _a2a_state[key] = (src, out, h_src, h_out, streams, {})
     return _a2a_state[key]
 
@@ -249,8 +249,9 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     head sharding communication-free (flash_attention_v1/CUDA/flash_attention_v1.h:170-172) is what allows it.
 
     transport "peer" (CUDA default): rows are staged once in symmetric memory; each rank PULLS the blocks it needs with
-      copy-engine 2-D copies (fa_copy_2d_async) on side streams, `chunks` head groups deep, so the pulls of group c+1
-      hide under the attention kernel of group c; outputs are pulled back the same way after one barrier.
+      copy-engine 2-D copies (fa_copy_2d_async) on side streams, in up to `chunks` head groups sized to the persistent
+      kernel's round quantisation (_a2a_chunk_plan), so the pulls of group c+1 and the output pulls of group c-1 hide
+      under the attention kernel of group c.
     transport "collective": two dist.all_to_all_single calls (any backend; used by the gloo CPU tests).
     attn_fn(q, k, v) -> o on [1,h,L,d] tensors defaults to ops.flash_attention_v1_ex(causal=causal).
     """
@@ -291,20 +292,23 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     src[1].copy_(K.reshape(BH, Ls, d))
     src[2].copy_(V.reshape(BH, Ls, d))
     h_src.barrier(channel=0)     # every rank's rows are staged (and every rank has left the previous call)
-    n_chunks = max(1, min(chunks, hpr))
-    bounds = [hpr * c // n_chunks for c in range(n_chunks + 1)]
+    bounds = _a2a_chunk_plan(hpr, L, chunks, Q.device)
+    n_chunks = len(bounds) - 1
     hc_max = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
     if "full" not in cache or cache["full"].shape[2] < hc_max:
         cache["full"] = torch.empty((2, 3, hc_max, L, d), dtype=Q.dtype, device=Q.device)
     full = cache["full"]
     peers = [h_src.get_buffer(p, src.shape, src.dtype) for p in range(world)]
+    outs = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype) for p in range(world)]
+    O = torch.empty((BH, Ls, d), dtype=Q.dtype, device=Q.device)
     h0 = rank * hpr
+    in_streams, out_stream = streams[:3], streams[3]
 
     def pull(c):
         """Rows of all ranks for head chunk c -> full[c % 2]; Q, K, V on separate copy streams."""
         hb, he = bounds[c], bounds[c + 1]
         events = []
-        for t, st in enumerate(streams):
+        for t, st in enumerate(in_streams):
             st.wait_stream(main)             # the kernel of chunk c-2, last reader of full[c % 2], is already enqueued
             for s in range(world):
                 p = (rank + s) % world       # start with the local block, then a different peer per rank
@@ -323,15 +327,63 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
             pending = pull(c + 1)            # travels while the kernel of chunk c runs
         q, k, v = (full[c % 2, t, :he - hb][None] for t in range(3))
         attn_fn(q, k, v, out_sym[hb:he][None])
-    h_out.barrier(channel=0)     # every rank's outputs are complete
-    O = torch.empty((BH, Ls, d), dtype=Q.dtype, device=Q.device)
-    outs = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype) for p in range(world)]
-    for s in range(world):
-        p = (rank + s) % world
-        st = streams[s % len(streams)]
-        st.wait_stream(main)
-        _copy_2d(O[p * hpr:(p + 1) * hpr], outs[p][:, rank * Ls:(rank + 1) * Ls], st)
-    for st in streams:
-        main.wait_stream(st)
-    h_out.barrier(channel=1)     # nobody restages or overwrites outputs while a peer may still be pulling them
+        # outputs of chunk c go home under the kernel of chunk c+1: the side stream waits for this rank's kernel, meets
+        # the other ranks (a device-side barrier on that stream, so the main stream never blocks on a peer), then pulls
+        # this rank's rows of every peer's chunk-c heads
+        out_stream.wait_stream(main)
+        with torch.cuda.stream(out_stream):
+            h_out.barrier(channel=c)
+            for s in range(world):
+                p = (rank + s) % world
+                _copy_2d(O[p * hpr + hb:p * hpr + he], outs[p][hb:he, rank * Ls:(rank + 1) * Ls], out_stream)
+    main.wait_stream(out_stream)
+    h_out.barrier(channel=n_chunks)   # nobody restages or overwrites outputs while a peer may still be pulling them
     return O.reshape(B, H, Ls, d)
+
+
+def _a2a_chunk_plan(hpr: int, L: int, max_chunks: int, device) -> list:
+    sms = torch.cuda.get_device_properties(device).multi_processor_count if device.type == "cuda" else 1
+    return list(_a2a_plan(hpr, -(-L // 256), max(1, min(max_chunks, 4)), sms))
+
+
+import functools  # noqa: E402
+
+
+@functools.lru_cache(maxsize=64)
+def _a2a_plan(hpr: int, items_per_head: int, max_chunks: int, sms: int, pull_ratio: float = 0.5) -> tuple:
+    """Head-chunk boundaries for the pipelined exchange, by a small time model (unit: one round of the persistent kernel).
+    The attention kernel runs one CTA per SM over 256-row work items, so a chunk of h heads costs
+    ceil(h * items_per_head / SMs) rounds (32 heads at L = 16384 on 148 SMs: 8+8+8+8 costs 16 rounds, 9+14+9 costs 15,
+    one chunk 14).  Pulling a head's Q, K, V rows costs `pull_ratio` of its compute time (NVLink copy engines vs the
+    tensor pipe; 0.5 is conservative), its output a third of that.  The pull of chunk c+1 and the output pull of chunk
+    c-1 run under the kernel of chunk c; the first pull and the last output pull are exposed.  Minimises
+        pull(c0) + sum_c max(rounds(c), pull(c+1)) + out_pull(c_last)."""
+    head_rounds = items_per_head / sms
+    rounds = lambda h: -(-h * items_per_head // sms)
+    pull = lambda h: pull_ratio * h * head_rounds
+
+    def cost(sizes):
+        t = pull(sizes[0])
+        for i, h in enumerate(sizes):
+            t += max(rounds(h), pull(sizes[i + 1])) if i + 1 < len(sizes) else rounds(h)
+        return t + pull(sizes[-1]) / 3.0
+
+    best, best_cost = (hpr,), cost((hpr,))
+
+    def search(prefix, left, k):
+        nonlocal best, best_cost
+        if k == 1 or left == 1:
+            c = cost(prefix + (left,))
+            if c < best_cost - 1e-9:
+                best, best_cost = prefix + (left,), c
+            return
+        for h in range(1, left):
+            search(prefix + (h,), left - h, k - 1)
+        search(prefix, left, 1)
+
+    if hpr > 1 and max_chunks > 1:
+        search((), hpr, max_chunks)
+    out = [0]
+    for h in best:
+        out.append(out[-1] + h)
+    return tuple(out)

@@ -845,6 +845,18 @@ int fa_copy_2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, s
   return FA_OK;
 }
 
+// n such copies with common block shape and pitches, one call: the head exchange issues 8-32 of them per step and the
+// per-call cost of the Python -> ctypes path (10-20 us) would otherwise exceed the copies themselves.
+int fa_copy_2d_multi_async(int n, void* const* dst, size_t dpitch, const void* const* src, size_t spitch, size_t width,
+                           size_t height, void* stream) {
+  if (n < 0 || !dst || !src) return fail(FA_ERR_SHAPE, "fa_copy_2d_multi_async: bad arguments");
+  for (int i = 0; i < n; ++i) {
+    const int rc = fa_copy_2d_async(dst[i], dpitch, src[i], spitch, width, height, stream);
+    if (rc != FA_OK) return rc;
+  }
+  return FA_OK;
+}
+
 void fa_release_host_staging(void) {
   const int dev = current_device();
   if (dev < 0) return;

@@ -225,17 +225,6 @@ def _a2a_buffers(BH, hpr, Ls, L, d, dtype, device, group):
     return _a2a_state[key]
 
 
-def _copy_2d(dst, src, stream):
-    """dst, src: [n, rows, d] tensors whose [rows, d] blocks are dense and whose leading stride may differ (a row window of
-    a taller tensor): one cudaMemcpy2DAsync on `stream` — copy engines, no SMs."""
-    from . import _lib
-    n, rows, d = src.shape
-    es = src.element_size()
-    assert dst.shape == src.shape and dst.stride(-1) == 1 and src.stride(-1) == 1 and dst.stride(-2) == d and src.stride(-2) == d
-    _lib.check(_lib.load().fa_copy_2d_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
-                                            rows * d * es, n, stream.cuda_stream))
-
-
 def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=None, causal: bool = False,
                        transport: str = "auto", chunks: int = 4, attn_fn=None):
     """Attention over a sequence sharded across the ranks of `group`, by exchanging heads instead of circulating K/V.
@@ -249,7 +238,7 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     head sharding communication-free (flash_attention_v1/CUDA/flash_attention_v1.h:170-172) is what allows it.
 
     transport "peer" (CUDA default): rows are staged once in symmetric memory; each rank PULLS the blocks it needs with
-      copy-engine 2-D copies (fa_copy_2d_async) on side streams, in up to `chunks` head groups sized to the persistent
+      copy-engine 2-D copies (fa_copy_2d_multi_async) on side streams, in up to `chunks` head groups sized to the persistent
       kernel's round quantisation (_a2a_chunk_plan), so the pulls of group c+1 and the output pulls of group c-1 hide
       under the attention kernel of group c.
     transport "collective": two dist.all_to_all_single calls (any backend; used by the gloo CPU tests).
@@ -298,21 +287,47 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     if "full" not in cache or cache["full"].shape[2] < hc_max:
         cache["full"] = torch.empty((2, 3, hc_max, L, d), dtype=Q.dtype, device=Q.device)
     full = cache["full"]
-    peers = [h_src.get_buffer(p, src.shape, src.dtype) for p in range(world)]
-    outs = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype) for p in range(world)]
-    O = torch.empty((BH, Ls, d), dtype=Q.dtype, device=Q.device)
+    # Every block address of the exchange, computed once per (buffers, plan) and handed to the library as pointer arrays:
+    # one C call per (chunk, tensor) instead of one Python -> ctypes round trip per block.
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    es = Q.element_size()
     h0 = rank * hpr
+    plan_key = (tuple(bounds), full.data_ptr())
+    if cache.get("plan_key") != plan_key:
+        peer_ptr = [h_src.get_buffer(p, src.shape, src.dtype).data_ptr() for p in range(world)]
+        out_ptr = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype).data_ptr() for p in range(world)]
+        order = [(rank + s) % world for s in range(world)]     # the local block first, then a different peer per rank
+        arr = lambda xs: (ctypes.c_void_p * len(xs))(*xs)
+        plans = []
+        for c in range(n_chunks):
+            hb, he = bounds[c], bounds[c + 1]
+            ins = []
+            for t in range(3):
+                dst = [full[c % 2, t].data_ptr() + p * Ls * d * es for p in order]                         # [:, p*Ls:(p+1)*Ls]
+                srcs = [peer_ptr[p] + ((t * BH + h0 + hb) * Ls * d) * es for p in order]                   # [t, h0+hb:h0+he]
+                ins.append((arr(dst), arr(srcs)))
+            odst = [None] * world
+            osrc = [None] * world
+            for i, p in enumerate(order):
+                odst[i] = p * hpr + hb                                                                     # O[p*hpr+hb : p*hpr+he]
+                osrc[i] = out_ptr[p] + (hb * L + rank * Ls) * d * es                                       # outs[p][hb:he, rank*Ls:...]
+            plans.append((ins, odst, arr(osrc), he - hb))
+        cache["plan_key"], cache["plans"] = plan_key, plans
+    plans = cache["plans"]
+    O = torch.empty((BH, Ls, d), dtype=Q.dtype, device=Q.device)
     in_streams, out_stream = streams[:3], streams[3]
+    row_bytes = Ls * d * es
 
     def pull(c):
         """Rows of all ranks for head chunk c -> full[c % 2]; Q, K, V on separate copy streams."""
-        hb, he = bounds[c], bounds[c + 1]
+        ins, _, _, nh = plans[c]
         events = []
         for t, st in enumerate(in_streams):
             st.wait_stream(main)             # the kernel of chunk c-2, last reader of full[c % 2], is already enqueued
-            for s in range(world):
-                p = (rank + s) % world       # start with the local block, then a different peer per rank
-                _copy_2d(full[c % 2, t, :he - hb, p * Ls:(p + 1) * Ls], peers[p][t, h0 + hb:h0 + he], st)
+            _lib.check(lib.fa_copy_2d_multi_async(world, ins[t][0], L * d * es, ins[t][1], row_bytes, row_bytes, nh,
+                                                  st.cuda_stream))
             ev = torch.cuda.Event()
             ev.record(st)
             events.append(ev)
@@ -333,9 +348,11 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
         out_stream.wait_stream(main)
         with torch.cuda.stream(out_stream):
             h_out.barrier(channel=c)
-            for s in range(world):
-                p = (rank + s) % world
-                _copy_2d(O[p * hpr + hb:p * hpr + he], outs[p][hb:he, rank * Ls:(rank + 1) * Ls], out_stream)
+            _, odst, osrc, nh = plans[c]
+            o_base = O.data_ptr()
+            dst = (ctypes.c_void_p * world)(*[o_base + h * row_bytes for h in odst])
+            _lib.check(lib.fa_copy_2d_multi_async(world, dst, row_bytes, osrc, L * d * es, row_bytes, nh,
+                                                  out_stream.cuda_stream))
     main.wait_stream(out_stream)
     h_out.barrier(channel=n_chunks)   # nobody restages or overwrites outputs while a peer may still be pulling them
     return O.reshape(B, H, Ls, d)

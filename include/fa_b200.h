@@ -157,6 +157,9 @@ void fa_release_host_staging(void);   /* frees the CURRENT device's staging buff
  * by the sequence-parallel all-to-all path (sharding.alltoall_attention) to move [heads][rows][d] blocks between peer-
  * mapped buffers without taking SMs from the attention kernel. */
 int fa_copy_2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+/* n copies of the same block shape and pitches in one call (the exchange issues 8-32 per step). */
+int fa_copy_2d_multi_async(int n, void* const* dst, size_t dpitch, const void* const* src, size_t spitch, size_t width,
+                           size_t height, void* stream);
 
 /* Diagnostics: how many TMA tensor maps were served from the per-thread cache / had to be encoded by the driver since
  * the library was loaded (launching on the same buffers step after step must not re-encode; the reference re-derives

@@ -46,7 +46,7 @@ def test_two_gpu_head_sharding_nccl_gather():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    full, Q, K, V = q.get(timeout=300)
+    full, Q, K, V = _get_or_fail(q, procs, 240)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -71,6 +71,28 @@ def test_tensors_on_a_non_current_device():
     ref = reference.naive_attention_batched_f64(*(x.float().cpu().numpy() for x in (Q, K, V)))
     assert np.abs(O.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
     assert np.abs(O2.float().cpu().numpy().reshape(2, 300, 64) - ref).max() <= 2e-3
+
+
+def _get_or_fail(q, procs, timeout):
+    """q.get() that gives up as soon as a worker has died with an error (instead of sitting out the whole timeout while
+    the surviving rank hangs in a collective, which on a GPU box is minutes of billed time)."""
+    import queue
+    import time
+    t_end = time.time() + timeout
+    while time.time() < t_end:
+        try:
+            return q.get(timeout=2)
+        except queue.Empty:
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                pytest.fail(f"worker exited with code {dead[0].exitcode} before producing a result")
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    pytest.fail("workers timed out")
 
 
 def _ring_worker(rank, world, port, q, transport="nccl", causal=False):
@@ -117,7 +139,7 @@ def test_two_gpu_ring_attention(transport, causal):
     procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q, transport, causal)) for r in range(2)]
     for p in procs:
         p.start()
-    shards, Q, K, V = q.get(timeout=300)
+    shards, Q, K, V = _get_or_fail(q, procs, 240)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -171,7 +193,7 @@ def test_two_gpu_alltoall_attention(transport, causal):
     procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q, transport, causal)) for r in range(2)]
     for p in procs:
         p.start()
-    shards, Q, K, V = q.get(timeout=300)
+    shards, Q, K, V = _get_or_fail(q, procs, 240)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

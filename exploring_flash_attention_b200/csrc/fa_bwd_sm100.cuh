@@ -26,7 +26,8 @@
 //   and the softmax warps: T_h(j+1) is issued right behind acc_h(j), so the pipe works on one half while the softmax
 //   warps exponentiate the other (B200: +35..50 % over whole-tile hand-overs).
 //   TMEM: T1 [0,128) T2 [128,256) ACC0 [256,256+D) (dK | dQ) ACC1 [256+D,256+2D) (dV).
-//   warps 0-3 softmax + epilogue, warp 4 TMA producer (streamed pair double-buffered), warp 5 tcgen05.mma issuer.
+//   warps 0-3 / 4-7 softmax of column half 0 / 1 + epilogue, warp 8 TMA producer (streamed pair double-buffered),
+//   warp 9 tcgen05.mma issuer.
 // 16-bit dtypes, d in {64, 128}.  Causal: tiles strictly above the diagonal are skipped, the diagonal tile is masked.
 #pragma once
 #include <cuda_runtime.h>
@@ -104,12 +105,12 @@ struct BwdTraits {
   static constexpr int NUM_BARS = 1 + 2 + 2 + 2 + 2 + 1;
   static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES /*resident pair*/ + 4 * TILE_BYTES /*2 stages x streamed pair*/ +
                                     NUM_BARS * 8 + 16;
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 320;   // softmax warpgroup per column half (warps 0-3, 4-7), warp 8 TMA, warp 9 MMA
   static constexpr int TM_T1 = 0, TM_T2 = 128, TM_ACC0 = 256, TM_ACC1 = 256 + D;
 };
 
 template <int D, int DT, bool DKV>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
               const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
               const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1, const BwdParams p) {
@@ -142,7 +143,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
   const int j_end = (p.causal && !DKV) ? tile + 1 : n_tiles;
   const int n_iter = j_end - j_begin;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     mbar_init(r_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -155,7 +156,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmR0);
       tma_prefetch_desc(&tmR1);
@@ -172,7 +173,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (elect_one_sync()) {
       auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int row) {
@@ -190,7 +191,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
         load_tile(sS + (2 * st + 1) * TILE_BYTES, &tmS1, &s_full[st], (j_begin + it) * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer ========================================
     if (elect_one_sync()) {
       // The streamed tile is processed as two 64-row halves so the tensor pipe and the softmax warps ping-pong inside the
@@ -251,8 +252,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
     }
   } else {
     // ===================================== softmax + epilogue warps ===========================
-    const int row = warp * 32 + lane;                                 // TMEM lane = local row of the resident tile
-    const uint32_t t_lane = tmem_base + (uint32_t(warp * 32) << 16);
+    // Two softmax warpgroups, one per column half of T1/T2 (warps 0-3: half 0, warps 4-7: half 1): with one warp per SM
+    // sub-partition the exponentials issued at ~3.3 cycles per instruction and the tensor pipe sat at 36-48 %.
+    const int wg = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;                           // TMEM lane = local row of the resident tile
+    const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
     const size_t ws_head = size_t(bh) * p.Lp;
     float my_lse2 = 0.f, my_delta = 0.f;
     if (!DKV) {
@@ -264,8 +268,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       const bool diag = p.causal && (j == tile);
       const float* lse_col = p.lse2 + ws_head + j * 128;     // DKV: per-column (query) statistics of this streamed tile
       const float* delta_col = p.delta + ws_head + j * 128;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {   // columns [64h, 64h+64) belong to half h
+      {
+      const int h = wg;               // this warpgroup's column half: columns [64h, 64h+64)
       FA_BWD_WAIT(&t_full[h], it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -337,6 +341,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
         constexpr int CPB = BLK_ELEMS / 32;   // 32-column TMEM loads per 128-byte block: 2 (16-bit)
 #pragma unroll
         for (int h = 0; h < CPB; ++h) {
+          if ((((which * NBLK + b) * CPB + h) & 1) != wg) continue;   // the two warpgroups take alternate 32-column units
           uint32_t o[32];
           tmem_ld32(tA + b * BLK_ELEMS + h * 32, o);
           tc_wait_ld();
@@ -358,7 +363,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (storer) {
 #pragma unroll
       for (int which = 0; which < N_OUT; ++which)
@@ -372,7 +377,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace fa

@@ -465,7 +465,9 @@ def ring_checks(torch, dist, ops, rank, world, max_over_ranks, barrier):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/)
 NCU_TRAFFIC_BYTES: dict = {
-    "c2": {"bytes": 243_684_096, "source": "profiles/r1_fwd_c2_persistent_full.txt (201.45 MB read + 42.24 MB written)"},
+    "c2": {"bytes": 243_479_296, "source": "profiles/r2_fwd_c2_full.txt (201.39 MB read + 42.09 MB written; tensor pipe 59.6 %)"},
+    "c1": {"bytes": 113_222_400, "source": "profiles/r2_fwd_c1_full.txt (100.71 MB read + 12.51 MB written)"},
+    "c5": {"bytes": 2_130_111_648, "source": "profiles/r2_tiled_d_pair_c5_full.txt (1610.66 MB read + 519.45 MB written)"},
 }
 
 

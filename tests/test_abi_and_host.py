@@ -142,3 +142,21 @@ def test_host_entry_point_validates_before_touching_the_device():
             ops.flash_attention_host(q, bad, q)
         with pytest.raises(_lib.FlashAttentionError):
             ops.flash_attention_host(q, q, q, bad)
+
+
+def test_alltoall_chunk_plan_partitions_the_heads():
+    """sharding._a2a_plan: boundaries start at 0, end at the head count, strictly increase, respect the chunk limit; a
+    single chunk when splitting cannot help (one head, or a whole number of rounds already)."""
+    from exploring_flash_attention_b200.sharding import _a2a_plan
+    for hpr in (1, 2, 5, 16, 32, 37):
+        for items in (1, 4, 64):
+            for max_chunks in (1, 2, 4):
+                b = _a2a_plan(hpr, items, max_chunks, 148)
+                assert b[0] == 0 and b[-1] == hpr and all(x < y for x, y in zip(b, b[1:]))
+                assert len(b) - 1 <= max_chunks
+    assert _a2a_plan(1, 64, 4, 148) == (0, 1)
+    assert _a2a_plan(32, 64, 1, 148) == (0, 32)
+    # 32 heads x 64 items on 148 SMs: one chunk is 14 rounds; the plan may add at most one round of quantisation loss
+    b = _a2a_plan(32, 64, 4, 148)
+    rounds = sum(-(-(y - x) * 64 // 148) for x, y in zip(b, b[1:]))
+    assert rounds <= 15

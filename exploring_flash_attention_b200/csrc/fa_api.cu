@@ -428,7 +428,8 @@ int launch_tiled_d(const void* Q, const void* K, const void* V, void* O, int BH,
 
 // K2P: one CTA pair per 128-row q-tile (fa_tiled_d_pair_sm100.cuh).
 template <int D, int DT>
-int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream) {
+int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, int BH, int L, cudaStream_t stream,
+                        float* lse_out = nullptr, int causal = 0) {
   using T = fa::TiledDPairTraits<D, DT>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
@@ -444,6 +445,8 @@ int launch_tiled_d_pair(const void* Q, const void* K, const void* V, void* O, in
   p.n_splits = 1;
   p.scale = 1.0f / std::sqrt(float(D));
   p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse_out = lse_out;
+  p.causal = causal;
   auto kern = fa::fa_tiled_d_pair_kernel<D, DT>;
   static SmemAttrOnce smem_attr;
   if ((rc = smem_attr.ensure(kern, T::SMEM_BYTES)) != FA_OK) return rc;
@@ -617,8 +620,14 @@ int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float
     TiledDExtra tx;
     tx.lse_out = LSE;
     tx.causal = (flags & FA_FLAG_CAUSAL) ? 1 : 0;
-    if (tx.lse_out == nullptr && !tx.causal) return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, static_cast<cudaStream_t>(stream));
-    return dispatch_tiled_d_slab(Q, K, V, O, B * H, L, d, dtype, static_cast<cudaStream_t>(stream), tx);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (tx.lse_out == nullptr && !tx.causal) return dispatch_tiled_d(Q, K, V, O, B * H, L, d, dtype, s);
+    // 16-bit d = 512: the CTA-pair kernel serves causal masking and the LSE output itself
+    if (tiled_d_pair_mode() >= 1 && d == 512 && dtype == fa::DT_BF16)
+      return launch_tiled_d_pair<512, fa::DT_BF16>(Q, K, V, O, B * H, L, s, tx.lse_out, tx.causal);
+    if (tiled_d_pair_mode() >= 1 && d == 512 && dtype == fa::DT_F16)
+      return launch_tiled_d_pair<512, fa::DT_F16>(Q, K, V, O, B * H, L, s, tx.lse_out, tx.causal);
+    return dispatch_tiled_d_slab(Q, K, V, O, B * H, L, d, dtype, s, tx);
   }
   return dispatch_fwd<false>(Q, K, V, O, B * H, L, d, dtype, L, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream),
                              LSE, (flags & FA_FLAG_CAUSAL) ? 1 : 0);

@@ -108,7 +108,9 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int n_qtiles = (p.L + T::BM - 1) / T::BM;
   const int q_row0 = (pair % n_qtiles) * T::BM + int(rank) * T::BMC;   // first query row of THIS CTA
   const int bh = pair / n_qtiles;
-  const int n_tiles = (p.L + BN - 1) / BN;
+  // causal: nothing right of this q-tile's diagonal block is loaded (both CTAs of the pair walk the same KV tiles)
+  const int kv_end = p.causal ? min(p.L, (pair % n_qtiles) * T::BM + T::BM) : p.L;
+  const int n_tiles = (kv_end + BN - 1) / BN;
   // (Tried and dropped: starting each q-tile's KV loop at a different tile so the q-tiles of a head do not pull the same
   //  K/V lines out of L2 at the same time — no measurable change, 1031 vs 1039 TFLOP/s at B16 H8 L4096 d512.)
 
@@ -262,7 +264,10 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tmem_ld32(tS + 32, s[1]);
       tc_wait_ld();
 
-      const int valid = p.L - (j * BN + half * 64);   // keys of this thread's half that exist
+      // keys of this thread's half that its row may attend to: the ragged end of the keys and, when causal, the diagonal
+      // (a row's right half can be masked out entirely; its left half never is: key j*BN <= the row index on the diagonal)
+      int valid = kv_end - (j * BN + half * 64);
+      if (p.causal) valid = min(valid, q_row0 + row - (j * BN + half * 64) + 1);
       if (valid < 64) {
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -369,7 +374,10 @@ fa_tiled_d_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ------------------------------- epilogue: O / l -> 16-bit -> smem (Q's dead blocks) -> TMA store ------------
     l_buf[t] = l;
     named_bar_sync(1, 128);
-    const float inv_l = 1.0f / (l + l_buf[t ^ 64]);
+    const float l_row = l + l_buf[t ^ 64];
+    const float inv_l = 1.0f / l_row;
+    if (p.lse_out != nullptr && half == 0 && q_row0 + row < p.L)
+      p.lse_out[size_t(bh) * p.L + q_row0 + row] = m_used * p.scale + __logf(l_row);
     mbar_wait_sleep(&pv_done[b_prev], par_prev);   // the last PV (same parity argument as in the rescale branch)
     tc_fence_after();
 #pragma unroll 1

@@ -59,8 +59,8 @@ int fa_v1_forward(const void* Q, const void* K, const void* V, void* O, int B, i
  * flash_attention_v1/README_v1.md:169).  Same kernel as fa_v1_forward plus:
  *   LSE   optional [B*H*L] fp32 output: log(sum_j exp(q_i.k_j / sqrt(d))) per query row (NULL to skip);
  *   flags FA_FLAG_CAUSAL: query row i attends to keys 0..i only (KV tiles above the diagonal are never loaded).
- * Every (d, dtype) fa_v1_forward serves; rows of 512-1024 bytes (16-bit d = 256/512, fp32 d = 128/256) run on the slab
- * tiled-d kernel when LSE or a flag is given. */
+ * Every (d, dtype) fa_v1_forward serves; rows of 512-1024 bytes run on the tiled-d kernels (16-bit d = 512 on the CTA-
+ * pair kernel, 16-bit d = 256 and fp32 d = 128/256 on the slab kernel). */
 #define FA_FLAG_CAUSAL 1u
 int fa_v1_forward_ex(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int L, int d,
                      int dtype, unsigned flags, void* stream);

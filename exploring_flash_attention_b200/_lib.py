@@ -37,6 +37,7 @@ SYMBOLS = {
     "fa_forward_host": (c_int, [c_int] + [c_void_p] * 4 + [c_int] * 6),
     "fa_copy_2d_async": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "fa_copy_2d_multi_async": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    "fa_copy_multi_async": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fa_release_host_staging": (None, []),
     "fa_debug_map_cache_stats": (None, [c_void_p, c_void_p]),
 }

@@ -866,6 +866,15 @@ int fa_copy_2d_multi_async(int n, void* const* dst, size_t dpitch, const void* c
   return FA_OK;
 }
 
+// n contiguous copies of `bytes` each (cudaMemcpyAsync, cudaMemcpyDefault): plain 1-D copies are the ones the copy
+// engines run beside a persistent kernel; the strided form above did not overlap with it on B200.
+int fa_copy_multi_async(int n, void* const* dst, const void* const* src, size_t bytes, void* stream) {
+  if (n < 0 || !dst || !src || bytes == 0) return fail(FA_ERR_SHAPE, "fa_copy_multi_async: bad arguments");
+  for (int i = 0; i < n; ++i)
+    FA_CUDA_TRY(cudaMemcpyAsync(dst[i], src[i], bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return FA_OK;
+}
+
 void fa_release_host_staging(void) {
   const int dev = current_device();
   if (dev < 0) return;

@@ -285,16 +285,24 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     n_chunks = len(bounds) - 1
     hc_max = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
     if "full" not in cache or cache["full"].shape[2] < hc_max:
+        # recv: blocks as they arrive, one contiguous [hc, Ls, d] block per (tensor, peer); full: the same rows regrouped
+        # per head over the whole sequence (what the kernel reads); ofull: the kernel's output before it is regrouped by
+        # destination rank into the symmetric buffer
+        cache["recv"] = torch.empty((2, 3, world, hc_max, Ls, d), dtype=Q.dtype, device=Q.device)
         cache["full"] = torch.empty((2, 3, hc_max, L, d), dtype=Q.dtype, device=Q.device)
-    full = cache["full"]
+        cache["ofull"] = torch.empty((2, hc_max, L, d), dtype=Q.dtype, device=Q.device)
+    recv, full, ofull = cache["recv"], cache["full"], cache["ofull"]
+    out_by_rank = out_sym.view(world, hpr, Ls, d)      # same bytes as [hpr, L, d]: [dest rank][head][row][d]
     # Every block address of the exchange, computed once per (buffers, plan) and handed to the library as pointer arrays:
-    # one C call per (chunk, tensor) instead of one Python -> ctypes round trip per block.
+    # one C call per (chunk, tensor) instead of one Python -> ctypes round trip per block.  All blocks are CONTIGUOUS on
+    # both sides (plain cudaMemcpyAsync): strided 2-D copies did not run beside the persistent kernel (8 GPUs, C4: the
+    # 1.05 ms of pulls stayed fully exposed), 1-D copies do; the regrouping is two small local copy kernels per chunk.
     import ctypes
     from . import _lib
     lib = _lib.load()
     es = Q.element_size()
     h0 = rank * hpr
-    plan_key = (tuple(bounds), full.data_ptr())
+    plan_key = (tuple(bounds), recv.data_ptr())
     if cache.get("plan_key") != plan_key:
         peer_ptr = [h_src.get_buffer(p, src.shape, src.dtype).data_ptr() for p in range(world)]
         out_ptr = [h_out.get_buffer(p, out_sym.shape, out_sym.dtype).data_ptr() for p in range(world)]
@@ -305,14 +313,11 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
             hb, he = bounds[c], bounds[c + 1]
             ins = []
             for t in range(3):
-                dst = [full[c % 2, t].data_ptr() + p * Ls * d * es for p in order]                         # [:, p*Ls:(p+1)*Ls]
+                dst = [recv[c % 2, t, p].data_ptr() for p in order]                                        # [hc, Ls, d]
                 srcs = [peer_ptr[p] + ((t * BH + h0 + hb) * Ls * d) * es for p in order]                   # [t, h0+hb:h0+he]
                 ins.append((arr(dst), arr(srcs)))
-            odst = [None] * world
-            osrc = [None] * world
-            for i, p in enumerate(order):
-                odst[i] = p * hpr + hb                                                                     # O[p*hpr+hb : p*hpr+he]
-                osrc[i] = out_ptr[p] + (hb * L + rank * Ls) * d * es                                       # outs[p][hb:he, rank*Ls:...]
+            odst = [p * hpr + hb for p in order]                                                           # O[p*hpr+hb : p*hpr+he]
+            osrc = [out_ptr[p] + ((rank * hpr + hb) * Ls * d) * es for p in order]                         # peer's [rank, hb:he]
             plans.append((ins, odst, arr(osrc), he - hb))
         cache["plan_key"], cache["plans"] = plan_key, plans
     plans = cache["plans"]
@@ -321,13 +326,12 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     row_bytes = Ls * d * es
 
     def pull(c):
-        """Rows of all ranks for head chunk c -> full[c % 2]; Q, K, V on separate copy streams."""
+        """Blocks of all ranks for head chunk c -> recv[c % 2]; Q, K, V on separate copy streams."""
         ins, _, _, nh = plans[c]
         events = []
         for t, st in enumerate(in_streams):
-            st.wait_stream(main)             # the kernel of chunk c-2, last reader of full[c % 2], is already enqueued
-            _lib.check(lib.fa_copy_2d_multi_async(world, ins[t][0], L * d * es, ins[t][1], row_bytes, row_bytes, nh,
-                                                  st.cuda_stream))
+            st.wait_stream(main)             # the regrouping copy of chunk c-2, last reader of recv[c % 2], is already enqueued
+            _lib.check(lib.fa_copy_multi_async(world, ins[t][0], ins[t][1], nh * row_bytes, st.cuda_stream))
             ev = torch.cuda.Event()
             ev.record(st)
             events.append(ev)
@@ -336,23 +340,26 @@ def alltoall_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, group=
     pending = pull(0)
     for c in range(n_chunks):
         hb, he = bounds[c], bounds[c + 1]
+        nh = he - hb
         for ev in pending:
             main.wait_event(ev)
+        for t in range(3):       # [peer][head][Ls][d] -> [head][peer*Ls + row][d]
+            full[c % 2, t, :nh].view(nh, world, Ls, d).copy_(recv[c % 2, t, :, :nh].permute(1, 0, 2, 3))
         if c + 1 < n_chunks:
             pending = pull(c + 1)            # travels while the kernel of chunk c runs
-        q, k, v = (full[c % 2, t, :he - hb][None] for t in range(3))
-        attn_fn(q, k, v, out_sym[hb:he][None])
+        q, k, v = (full[c % 2, t, :nh][None] for t in range(3))
+        attn_fn(q, k, v, ofull[c % 2, :nh][None])
+        out_by_rank[:, hb:he].copy_(ofull[c % 2, :nh].view(nh, world, Ls, d).permute(1, 0, 2, 3))
         # outputs of chunk c go home under the kernel of chunk c+1: the side stream waits for this rank's kernel, meets
         # the other ranks (a device-side barrier on that stream, so the main stream never blocks on a peer), then pulls
         # this rank's rows of every peer's chunk-c heads
         out_stream.wait_stream(main)
         with torch.cuda.stream(out_stream):
             h_out.barrier(channel=c)
-            _, odst, osrc, nh = plans[c]
+            _, odst, osrc, _ = plans[c]
             o_base = O.data_ptr()
             dst = (ctypes.c_void_p * world)(*[o_base + h * row_bytes for h in odst])
-            _lib.check(lib.fa_copy_2d_multi_async(world, dst, row_bytes, osrc, L * d * es, row_bytes, nh,
-                                                  out_stream.cuda_stream))
+            _lib.check(lib.fa_copy_multi_async(world, dst, osrc, nh * row_bytes, out_stream.cuda_stream))
     main.wait_stream(out_stream)
     h_out.barrier(channel=n_chunks)   # nobody restages or overwrites outputs while a peer may still be pulling them
     return O.reshape(B, H, Ls, d)

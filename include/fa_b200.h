@@ -161,6 +161,10 @@ int fa_copy_2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, s
 int fa_copy_2d_multi_async(int n, void* const* dst, size_t dpitch, const void* const* src, size_t spitch, size_t width,
                            size_t height, void* stream);
 
+/* n contiguous copies of `bytes` each in one call (cudaMemcpyAsync): what sharding.alltoall_attention pulls peer blocks
+ * with — 1-D copies run on the copy engines beside the persistent attention kernel, strided ones did not. */
+int fa_copy_multi_async(int n, void* const* dst, const void* const* src, size_t bytes, void* stream);
+
 /* Diagnostics: how many TMA tensor maps were served from the per-thread cache / had to be encoded by the driver since
  * the library was loaded (launching on the same buffers step after step must not re-encode; the reference re-derives
  * its launch state on every call, flash_attention_v1.h:280-292).  Either pointer may be NULL. */

@@ -261,13 +261,28 @@ def flash_attention_v2_combine(Oaccum, LSEaccum, out_dtype, shape, O=None):
 
 @_on_device_of
 def flash_attention_v2(Q, K, V, kv_per_split: int, O=None, workspace=None, sync: bool = False):
-    """Split-KV forward + combine. `workspace` = (Oaccum, LSEaccum) from v2_workspace(), reused across calls."""
+    """Split-KV forward + combine. `workspace` = (Oaccum, LSEaccum) from v2_workspace(), reused across calls.
+    (Validates once and makes the two library calls itself: at the reference's C3 size the two kernels take 25 us and
+    every avoidable microsecond of host work per call shows.)"""
     Q, K, V = _prep(Q, K, V)
     B, H, L, d = Q.shape
+    S = -(-L // kv_per_split) if kv_per_split > 0 else 0          # = fa_v2_num_splits(L, kv_per_split)
+    if S <= 0:
+        raise _lib.FlashAttentionError(-1, "kv_per_split must be positive")
     if workspace is None:
-        workspace = v2_workspace(B, H, L, d, kv_per_split, Q.device)
-    Oaccum, LSEaccum = flash_attention_v2_splitkv(Q, K, V, kv_per_split, *workspace)
-    O = flash_attention_v2_combine(Oaccum, LSEaccum, Q.dtype, (B, H, L, d), O)
+        Oaccum = torch.empty((S, B * H, L, d), dtype=torch.float32, device=Q.device)
+        LSEaccum = torch.empty((S, B * H, L), dtype=torch.float32, device=Q.device)
+    else:
+        # a reused workspace must hold exactly this call's splits: the kernel writes n_splits*B*H*L rows into it
+        Oaccum, LSEaccum = workspace
+        _check_buffer(Oaccum, (S, B * H, L, d), torch.float32, Q.device, "Oaccum")
+        _check_buffer(LSEaccum, (S, B * H, L), torch.float32, Q.device, "LSEaccum")
+    O = _out_like(O, Q)
+    lib = _lib.load()
+    dt, st = _DTYPES[Q.dtype], _stream()
+    _lib.check(lib.fa_v2_splitkv_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), Oaccum.data_ptr(), LSEaccum.data_ptr(),
+                                         B, H, L, d, kv_per_split, dt, st))
+    _lib.check(lib.fa_v2_combine(Oaccum.data_ptr(), LSEaccum.data_ptr(), O.data_ptr(), B, H, L, d, S, dt, st))
     if sync:
         torch.cuda.current_stream().synchronize()
     return O

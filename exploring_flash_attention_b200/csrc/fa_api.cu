@@ -135,6 +135,7 @@ int encode_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH,
 // A tensor map is a pure function of (pointer, dtype, shape, box, layout): callers that launch on the same buffers step
 // after step (every training / serving loop) get it from a small per-thread direct-mapped cache instead of a driver call
 // per operand per launch (the reference re-derives all launch state per call, flash_attention_v1.h:280-292).
+// 32 sets x 4 ways, round-robin replacement inside a set.
 struct MapKey {
   const void* ptr;
   long long head_stride_rows;
@@ -149,23 +150,29 @@ struct MapSlot {
   bool valid = false;
   alignas(64) CUtensorMap map;
 };
-constexpr int kMapCacheSlots = 64;
+constexpr int kMapCacheSets = 32, kMapCacheWays = 4;   // 4-way sets: the 4-7 operands of one launch never evict each other
 std::atomic<unsigned long long> g_map_hits{0}, g_map_misses{0};
 
 int make_map(CUtensorMap* m, const void* ptr, int dtype, int D, int L, int BH, int box_rows, bool mn_major_operand = false,
              long long head_stride_rows = 0 /* rows between consecutive heads; 0 = L (dense) */) {
-  thread_local MapSlot cache[kMapCacheSlots];
+  thread_local MapSlot cache[kMapCacheSets][kMapCacheWays];
+  thread_local unsigned char next_way[kMapCacheSets] = {};
   const MapKey key{ptr, head_stride_rows, dtype, D, L, BH, box_rows, mn_major_operand ? 1 : 0};
   unsigned long long h = reinterpret_cast<uintptr_t>(ptr) >> 8;
   h = (h ^ (h >> 17)) * 0x9E3779B97F4A7C15ull + (unsigned long long)(box_rows * 31 + (mn_major_operand ? 7 : 0) + L * 131 + BH);
-  MapSlot& slot = cache[(h >> 20) % kMapCacheSlots];
-  if (slot.valid && slot.key == key) {
-    *m = slot.map;
-    g_map_hits.fetch_add(1, std::memory_order_relaxed);
-    return FA_OK;
+  const int set = int((h >> 20) % kMapCacheSets);
+  for (int w = 0; w < kMapCacheWays; ++w) {
+    MapSlot& slot = cache[set][w];
+    if (slot.valid && slot.key == key) {
+      *m = slot.map;
+      g_map_hits.fetch_add(1, std::memory_order_relaxed);
+      return FA_OK;
+    }
   }
   const int rc = encode_map(m, ptr, dtype, D, L, BH, box_rows, mn_major_operand, head_stride_rows);
   if (rc != FA_OK) return rc;
+  MapSlot& slot = cache[set][next_way[set]];
+  next_way[set] = (unsigned char)((next_way[set] + 1) % kMapCacheWays);
   slot.key = key;
   slot.map = *m;
   slot.valid = true;
